@@ -1,0 +1,93 @@
+"""ctypes binding of libg2pc.so (the C-ABI CUDA library declared in include/g2pc.h).
+
+This is the stub a maintainer of the reference would add in place of
+`from gaussian_pointcloud_rasterization import _C` (gaussian_pointcloud_rasterization/__init__.py:14) and of
+the torch call chains in gauss_to_pc.py:140-275.  There is NO fallback: if the library is missing or a call
+fails, an exception is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libg2pc.so")
+
+F32, F64 = 0, 1
+CULL_EPS_NORM, CULL_EXPLICIT = 0, 1
+ST_OVERFLOW, ST_CHOLFAIL, ST_CHOLREG, ST_WORDS = 0, 1, 2, 4
+
+_c_void_p = ctypes.c_void_p
+_i32, _i64, _u32, _u64, _f32 = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_float
+
+# name -> argtypes, exactly as declared in include/g2pc.h
+SIGNATURES = {
+    "g2pc_version": ([], ctypes.c_int),
+    "g2pc_last_error": ([], ctypes.c_char_p),
+    "g2pc_cov_build": ([_c_void_p, _c_void_p, ctypes.c_int, _f32, _i64, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_normals": ([_c_void_p, _c_void_p, ctypes.c_int, _i64, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_eigvals_sym3": ([_c_void_p, _i64, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_sample_count": ([_c_void_p, _c_void_p, _c_void_p, ctypes.c_int, _c_void_p, _c_void_p, _i64, _i64,
+                           _c_void_p, _i32, _i32, _i32, _f32, _i32, _u64, _u32, _c_void_p, _c_void_p, _c_void_p,
+                           _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_sample_emit": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _i32, _u64, _u32, _c_void_p,
+                          _c_void_p, _c_void_p, ctypes.c_int, _i64, _c_void_p], ctypes.c_int),
+    "g2pc_dump_eps": ([_c_void_p, _i64, _i32, _i32, _u64, _u32, _c_void_p, _c_void_p], ctypes.c_int),
+}
+
+_lib = None
+
+
+class G2pcError(RuntimeError):
+    pass
+
+
+def load(path=None):
+    """Load libg2pc.so and attach the argument types.  Raises if the library is absent (no fallback)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise G2pcError(
+            f"{path} not found: build it with `python -m g2pc.build` (or __graft_entry__.build()). "
+            "There is no CPU fallback for the g2pc kernels.")
+    lib = ctypes.CDLL(path)
+    for name, (argtypes, restype) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().g2pc_last_error()
+        raise G2pcError(f"{what} failed (status {status}): {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def dtype_code(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.float64:
+        return F64
+    raise G2pcError(f"unsupported dtype {t.dtype} (need float32 or float64)")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise G2pcError("g2pc kernels need CUDA tensors; there is no CPU fallback "
+                            f"(got a tensor on {t.device})")

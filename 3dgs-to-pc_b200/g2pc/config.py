@@ -1,0 +1,23 @@
+"""Run-time defaults of the g2pc host layer (module attributes; change them before calling the drop-in API)."""
+import torch
+
+# Base seed of the Philox stream (key); counter = (global Gaussian id, sample, attempt, call id).
+SEED = 42
+
+# Accept test of the Mahalanobis cull: 1 = explicit sqrt(d^T Sigma^-1 d) <= std in fp32, as the reference computes
+# it (gauss_to_pc.py:92-103); 0 = |eps| <= std (equal in exact arithmetic, cheaper).
+CULL_MODE = 1
+
+# dtype of the colour / normal outputs of generate_pointcloud.  The reference returns float64 for both (an artefact
+# of torch.cat type promotion, gauss_to_pc.py:317-318,352-369) and casts to u8 / f4 when writing the PLY
+# (gauss_dataloader.py:176-200); float32 halves the output traffic and leaves the PLY bytes unchanged.
+OUTPUT_DTYPE = torch.float32
+
+# Dense attempts stored by the count pass; attempts beyond this only flag an overflow (re-run with more).
+MAX_ATTEMPTS_STORED = 32
+
+# python-renderer tile parameters.  The reference derives them from free GPU memory at call time
+# (gauss_render.py:440-444), which makes results hardware dependent; they are pinned to render()'s own defaults
+# (gauss_render.py:266).
+MAX_TILE_SIZE = 60
+MAX_GAUSSIANS_PER_TILE = 60000

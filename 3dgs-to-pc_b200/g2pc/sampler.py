@@ -1,0 +1,203 @@
+"""Host side of S2 (sampling + Mahalanobis cull): bin planning and kernel driver.
+
+The reference does its bin planning on the host too (gauss_to_pc.py:308-343: torch.unique / bincount / numpy
+gradient heuristic), then loops over bins and attempts from Python.  Here the host only turns the
+points-per-Gaussian histogram into two small tables (tiles, units); all per-Gaussian work happens in two kernels
+(g2pc_sample_count, g2pc_sample_emit; csrc/s2_sample.cu).
+"""
+import math
+import threading
+
+import numpy as np
+import torch
+
+from . import capi, config
+
+_call_counter = 0
+_call_lock = threading.Lock()
+
+
+def next_call_id():
+    """Each sampling call gets its own RNG sub-stream (4th Philox counter word)."""
+    global _call_counter
+    with _call_lock:
+        c = _call_counter
+        _call_counter += 1
+    return c
+
+
+def reset_call_counter(value=0):
+    global _call_counter
+    with _call_lock:
+        _call_counter = value
+
+
+# ------------------------------------------------------------------------------------------------------------
+def calculate_bin_sizes_from_hist(hist_nonzero):
+    """Bin-width heuristic of the reference (gauss_to_pc.py:105-138) evaluated on the host from the histogram of
+    points-per-Gaussian (counts of the occurring values, ascending).  Returns (start_bin, bin_size).
+    Raises ValueError for fewer than two distinct values, as numpy.gradient does in the reference."""
+    dist = np.asarray(hist_nonzero)
+    second = np.absolute(np.gradient(np.gradient(dist)))
+    bin_size = max(len(dist) // 100, 1)
+    usable = len(second) - len(second) % bin_size
+    per_bin = second[:usable].reshape(-1, bin_size).sum(axis=1)
+    cut_off = np.max(per_bin) // 50
+    peak = int(np.argmax(per_bin))
+    quiet = np.nonzero(per_bin[peak:] < cut_off)[0]
+    start_bin = int(quiet[0]) if quiet.shape[0] != 0 else 1
+    return start_bin, bin_size
+
+
+def plan_bins(hist, exact_num_points):
+    """hist[v] = number of Gaussians assigned v points.  Returns the reference's bins in loop order as a list of
+    (start, end, n, count) where Gaussians with start <= ppg < end all receive n points
+    (n = floor(start + (end - start) / 2), gauss_to_pc.py:326-337).  Bins with n <= 0 or count == 0 are dropped
+    (:339-343)."""
+    hist = np.asarray(hist)
+    values = np.nonzero(hist)[0]
+    if values.size == 0:
+        return []
+    if exact_num_points:
+        edges = values.astype(np.float64)
+    else:
+        start_bin, bin_size = calculate_bin_sizes_from_hist(hist[values])
+        head = values[:start_bin].astype(np.float32)
+        tail = np.unique(np.ceil(values[start_bin:].astype(np.float32) / np.float32(bin_size))) * np.float32(bin_size)
+        edges = np.concatenate([head, tail.astype(np.float32)]).astype(np.float64)
+    csum = np.concatenate([[0], np.cumsum(hist)])
+    bins = []
+    for i in range(edges.shape[0]):
+        start = float(edges[i])
+        end = float(edges[i + 1]) if i != edges.shape[0] - 1 else start + 1
+        n = math.floor(start + (end - start) / 2)
+        if n <= 0:
+            continue
+        lo = min(max(int(math.ceil(start)), 0), hist.shape[0])
+        hi = min(max(int(math.ceil(end)), 0), hist.shape[0])
+        count = int(csum[hi] - csum[lo]) if hi > lo else 0
+        if count < 1:
+            continue
+        bins.append((start, end, n, count))
+    return bins
+
+
+def _lpg_for(k):
+    """Threads cooperating on one Gaussian: each draws at most ~8 samples per attempt."""
+    if k <= 8:
+        return 1
+    return min(256, 1 << int(math.ceil(math.log2(k / 8.0))))
+
+
+class SamplePlan:
+    """Tile and unit tables for one sampling call (see include/g2pc.h: g2pc_tile_t, g2pc_unit_t)."""
+
+    def __init__(self, bin_k_count, attempts_stored, include_centres=True):
+        """bin_k_count: list of (k, count) in output order; Gaussians of bin b occupy bin-order indices
+        [J0_b, J0_b + count_b)."""
+        tiles, units, unit_src = [], [], []
+        j0 = 0
+        tile_base_index = 0
+        centre_lens = []
+        A = attempts_stored
+        for (k, count) in bin_k_count:
+            lpg = _lpg_for(k)
+            per_tile = 256 // lpg
+            nt = (count + per_tile - 1) // per_tile
+            starts = j0 + np.arange(nt, dtype=np.int64) * per_tile
+            counts = np.minimum(per_tile, j0 + count - starts)
+            t = np.stack([starts, counts, np.full(nt, k), np.full(nt, lpg)], axis=1)
+            tiles.append(t)
+            if include_centres:
+                units.append(np.array([[-1, j0, count, 0]], dtype=np.int64))
+                unit_src.append(np.array([-(len(centre_lens) + 1)], dtype=np.int64))
+                centre_lens.append(count)
+            if k > 0:
+                tidx = tile_base_index + np.arange(nt, dtype=np.int64)
+                for a in range(A):
+                    u = np.stack([np.full(nt, a), starts, counts, np.full(nt, k)], axis=1)
+                    units.append(u)
+                    unit_src.append(tidx * A + a)
+            tile_base_index += nt
+            j0 += count
+        self.n = j0
+        self.attempts_stored = A
+        self.tiles = (np.concatenate(tiles, 0) if tiles else np.zeros((0, 4))).astype(np.int32)
+        self.units = (np.concatenate(units, 0) if units else np.zeros((0, 4))).astype(np.int32)
+        src = np.concatenate(unit_src, 0) if unit_src else np.zeros((0,), dtype=np.int64)
+        # lengths are gathered from concat([tile_totals (num_tiles*A), centre_lens]); negative src -> centre slot
+        nt_total = self.tiles.shape[0]
+        self.unit_src = np.where(src >= 0, src, nt_total * A + (-src - 1)).astype(np.int64)
+        self.centre_lens = np.asarray(centre_lens, dtype=np.int64)
+        self.capacity = int(sum(c * (k + (1 if include_centres else 0)) for (k, c) in bin_k_count))
+
+
+def run_plan(plan, xyz, cov, colours, normals, perm, num_attempts, std, seed, call_id, gid_offset=0,
+             out_dtype=None, cull_mode=None, want_normals=True):
+    """Launch the two S2 kernels for `plan`.  All tensors on one CUDA device.  Returns
+    (points, colours, normals|None, total_tensor, status_tensor) with outputs sized plan.capacity (valid rows:
+    [0, total))."""
+    lib = capi.load()
+    capi.require_cuda(xyz, cov, colours, normals, perm)
+    dev = xyz.device
+    out_dtype = out_dtype or config.OUTPUT_DTYPE
+    cull_mode = config.CULL_MODE if cull_mode is None else cull_mode
+    n = plan.n
+    A = plan.attempts_stored
+    nt = plan.tiles.shape[0]
+    nu = plan.units.shape[0]
+    st = capi.stream_ptr(dev)
+
+    assert xyz.dtype == torch.float32 and cov.dtype == torch.float32
+    xyz = xyz.contiguous()
+    cov = cov.contiguous()
+    colours = colours.contiguous()
+    if normals is not None:
+        normals = normals.contiguous().to(torch.float32)
+    perm = perm.to(torch.int32).contiguous()
+    assert perm.shape[0] == n
+
+    tiles_d = torch.from_numpy(plan.tiles).to(dev, non_blocking=True)
+    units_d = torch.from_numpy(plan.units).to(dev, non_blocking=True)
+    src_d = torch.from_numpy(plan.unit_src).to(dev, non_blocking=True)
+    centre_d = torch.from_numpy(plan.centre_lens).to(dev, non_blocking=True)
+
+    records = torch.empty((max(n, 1), 16), dtype=torch.float32, device=dev)
+    xl = torch.empty((A, max(n, 1)), dtype=torch.int32, device=dev)
+    tile_totals = torch.zeros((max(nt, 1) * A,), dtype=torch.int32, device=dev)
+    status = torch.zeros((capi.ST_WORDS,), dtype=torch.int32, device=dev)
+
+    capi.check(lib.g2pc_sample_count(
+        capi.ptr(xyz), capi.ptr(cov), capi.ptr(colours), capi.dtype_code(colours), capi.ptr(normals),
+        capi.ptr(perm), int(gid_offset), n, capi.ptr(tiles_d), nt, int(num_attempts), A, float(std),
+        int(cull_mode), int(seed) & 0xFFFFFFFFFFFFFFFF, int(call_id) & 0xFFFFFFFF, capi.ptr(records), capi.ptr(xl),
+        capi.ptr(tile_totals), capi.ptr(status), st), "g2pc_sample_count")
+
+    lens = torch.cat([tile_totals[: nt * A].to(torch.int64), centre_d])[src_d]
+    unit_base = torch.zeros((nu + 1,), dtype=torch.int64, device=dev)
+    if nu:
+        torch.cumsum(lens, 0, out=unit_base[1:])
+
+    cap = plan.capacity
+    pts = torch.empty((max(cap, 1), 3), dtype=torch.float32, device=dev)
+    rgb = torch.empty((max(cap, 1), 3), dtype=out_dtype, device=dev)
+    nrm = torch.empty((max(cap, 1), 3), dtype=out_dtype, device=dev) if (want_normals and normals is not None) else None
+
+    capi.check(lib.g2pc_sample_emit(
+        capi.ptr(records), capi.ptr(xl), n, capi.ptr(units_d), capi.ptr(unit_base), nu,
+        int(seed) & 0xFFFFFFFFFFFFFFFF, int(call_id) & 0xFFFFFFFF, capi.ptr(pts), capi.ptr(rgb), capi.ptr(nrm),
+        capi.dtype_code(rgb), cap, st), "g2pc_sample_emit")
+    return pts, rgb, nrm, unit_base[nu], status, (records, xl, tile_totals, unit_base)
+
+
+def dump_eps(gids, k, attempt, seed, call_id=0):
+    """eps (k, n', 3) the sampler uses for Gaussians `gids` (int64 CUDA tensor) in `attempt` — for injecting the
+    kernel's stream into the reference / oracle in parity tests."""
+    lib = capi.load()
+    capi.require_cuda(gids)
+    gids = gids.to(torch.int64).contiguous()
+    eps = torch.empty((k, gids.shape[0], 3), dtype=torch.float32, device=gids.device)
+    capi.check(lib.g2pc_dump_eps(capi.ptr(gids), gids.shape[0], int(k), int(attempt),
+                                 int(seed) & 0xFFFFFFFFFFFFFFFF, int(call_id) & 0xFFFFFFFF, capi.ptr(eps),
+                                 capi.stream_ptr(gids.device)), "g2pc_dump_eps")
+    return eps
