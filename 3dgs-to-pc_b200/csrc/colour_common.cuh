@@ -1,0 +1,78 @@
+// colour_common.cuh — shared pieces of the colour stage (S3-S6): quadtree tables in shared memory, range queries.
+#pragma once
+#include "common.cuh"
+
+#define QT_FLAG_DROPPED 1
+#define QT_FLAG_BIG 2
+
+// node states written by the tree kernel
+#define NODE_NONE 0   // does not exist / dropped
+#define NODE_EMPTY 1  // exists, no Gaussian overlaps it (background fill, gauss_render.py:313-315)
+#define NODE_SPLIT 2  // exists and was split into 4 children (gauss_render.py:319-335)
+#define NODE_LEAF 3   // exists and is rendered
+
+struct QtMeta {
+    int32_t num_levels;  // tabulated levels 0..num_levels-1
+    int32_t max_gaussians_per_tile;
+    int32_t width, height;
+};
+
+// per-Gaussian projection record: 3 x float4
+//   q0 = (mx, my, c00', c01')     c' = conic * (-0.5 * log2(e));  c01' = (conic01 + conic10)'
+//   q1 = (c11', opacity, r, g)
+//   q2 = (b, depth, radius, valid)   valid: 1.0f if in front of the camera (gauss_render.py:167), else 0
+struct QtTables {
+    const int32_t* xs; const int32_t* xe; const int32_t* xf;
+    const int32_t* ys; const int32_t* ye; const int32_t* yf;
+};
+
+// copy the 1-D tables (6 arrays of n1 ints) into shared memory; returns pointers into smem
+__device__ __forceinline__ QtTables load_tables(const QtTables g, int n1, int32_t* smem) {
+    for (int i = threadIdx.x; i < n1; i += blockDim.x) {
+        smem[i] = g.xs[i];
+        smem[n1 + i] = g.xe[i];
+        smem[2 * n1 + i] = g.xf[i];
+        smem[3 * n1 + i] = g.ys[i];
+        smem[4 * n1 + i] = g.ye[i];
+        smem[5 * n1 + i] = g.yf[i];
+    }
+    __syncthreads();
+    QtTables s;
+    s.xs = smem; s.xe = smem + n1; s.xf = smem + 2 * n1;
+    s.ys = smem + 3 * n1; s.ye = smem + 4 * n1; s.yf = smem + 5 * n1;
+    return s;
+}
+
+// Members of the interval (rmin, rmax) among the 2^level nodes of one axis at `level`:
+//   min(rmax, e_i) > max(rmin, s_i)   (fp32 compares, strict — gauss_render.py:308-310)
+//   <=>  rmax > rmin  &&  rmax > s_i  &&  e_i > rmin  &&  e_i > s_i
+// starts / ends are non-decreasing within a level, so the candidates form the index range [lo, hi]; nodes inside the
+// range that are dropped or degenerate (e_i <= s_i) are filtered by the caller through axis_member().
+__device__ __forceinline__ void axis_range(const int32_t* __restrict__ s, const int32_t* __restrict__ e, int level,
+                                           float rmin, float rmax, int& lo, int& hi) {
+    const int n = 1 << level;
+    if (!(rmax > rmin)) { lo = 1; hi = 0; return; }
+    // first i with e_i > rmin
+    int a = 0, b = n;
+    while (a < b) { const int m = (a + b) >> 1; if ((float)e[m] > rmin) b = m; else a = m + 1; }
+    lo = a;
+    // last i with s_i < rmax
+    a = -1; b = n - 1;
+    while (a < b) { const int m = (a + b + 1) >> 1; if ((float)s[m] < rmax) a = m; else b = m - 1; }
+    hi = a;
+}
+
+__device__ __forceinline__ bool axis_member(const int32_t* __restrict__ s, const int32_t* __restrict__ e,
+                                            const int32_t* __restrict__ f, int i) {
+    return !(f[i] & QT_FLAG_DROPPED) && e[i] > s[i];
+}
+
+// rect of a Gaussian (gauss_render.py:182-193): [mean -+ radius] clipped to [0, W-1] x [0, H-1]
+__device__ __forceinline__ void gaussian_rect(float mx, float my, float radius, int W, int H, float& x0, float& x1,
+                                              float& y0, float& y1) {
+    const float wm = (float)W - 1.0f, hm = (float)H - 1.0f;
+    x0 = fminf(fmaxf(mx - radius, 0.0f), wm);
+    x1 = fminf(fmaxf(mx + radius, 0.0f), wm);
+    y0 = fminf(fmaxf(my - radius, 0.0f), hm);
+    y1 = fminf(fmaxf(my + radius, 0.0f), hm);
+}

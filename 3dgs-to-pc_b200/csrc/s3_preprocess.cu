@@ -1,0 +1,286 @@
+// s3_preprocess.cu — S3: per-camera, per-Gaussian projection + quadtree membership counting; S4b: instance emission.
+//
+// Reference semantics restated (not copied), renderer_type=python:
+//   gauss_render.py:101-148  build_covariance_2d   (EWA: cov2d = J W Sigma W^T J^T [:2,:2] + 0.3 I)
+//   gauss_render.py:151-168  projection_ndc        (p_h = [p,1] V P, p_w = 1/(w + 1e-6), in front <=> z_view <= -1e-6)
+//   gauss_render.py:171-193  get_radius / get_rect (radius = 3*ceil(sqrt(lambda_max)), rect clipped to the image)
+//   gauss_render.py:349      conic = inverse(cov2d)
+//   gauss_render.py:43-99    eval_sh (+0.5, clamp >= 0 as forward.cu:65-72) when SH coefficients are supplied
+//   gauss_render.py:301-319  tile membership: min(rect_max, tile_max) > max(rect_min, tile_min), strict, fp32
+// One thread per Gaussian.  Membership is evaluated by range queries on the per-level interval tables
+// (g2pc/quadtree.py) instead of testing every tile against every Gaussian.
+#include "colour_common.cuh"
+
+namespace {
+
+struct PreParams {
+    const float* xyz;
+    const float* cov;
+    const float* opacity;
+    const float* colours;  // (n,3) f32 or null
+    const float* shs;      // (n,3,sh_stride) f32 or null
+    int32_t sh_stride, sh_degree;
+    int64_t n;
+    g2pc_camera_t cam;
+    QtMeta meta;
+    QtTables tab;
+    int32_t n1;  // entries per 1-D table array
+    float4* proj;
+    uint32_t* node_cnt;
+};
+
+__device__ __forceinline__ int off2(int l) { return ((1 << (2 * l)) - 1) / 3; }
+
+__device__ __forceinline__ float3 sh_to_rgb(const float* __restrict__ sh, int stride, int deg, float3 d) {
+    // sh: 3 channels x stride coefficients (channel-major)
+    const float C0 = 0.28209479177387814f, C1 = 0.4886025119029199f;
+    const float C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f,
+                         0.5462742152960396f};
+    const float C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                         -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+    float out[3];
+    const float x = d.x, y = d.y, z = d.z;
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* s = sh + c * stride;
+        float r = C0 * s[0];
+        if (deg > 0) {
+            r = r - C1 * y * s[1] + C1 * z * s[2] - C1 * x * s[3];
+            if (deg > 1) {
+                r = r + C2[0] * xy * s[4] + C2[1] * yz * s[5] + C2[2] * (2.0f * zz - xx - yy) * s[6] +
+                    C2[3] * xz * s[7] + C2[4] * (xx - yy) * s[8];
+                if (deg > 2) {
+                    r = r + C3[0] * y * (3.0f * xx - yy) * s[9] + C3[1] * xy * z * s[10] +
+                        C3[2] * y * (4.0f * zz - xx - yy) * s[11] + C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * s[12] +
+                        C3[4] * x * (4.0f * zz - xx - yy) * s[13] + C3[5] * z * (xx - yy) * s[14] +
+                        C3[6] * x * (xx - 3.0f * yy) * s[15];
+                }
+            }
+        }
+        out[c] = fmaxf(r + 0.5f, 0.0f);
+    }
+    return make_float3(out[0], out[1], out[2]);
+}
+
+__global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
+    extern __shared__ int32_t smem_tab[];
+    const QtTables T = load_tables(p.tab, p.n1, smem_tab);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+
+    const float* V = p.cam.view;
+    const float* P = p.cam.proj;
+    const float m0 = p.xyz[3 * i], m1 = p.xyz[3 * i + 1], m2 = p.xyz[3 * i + 2];
+
+    // p_view = [mu, 1] @ V   (row-vector convention)
+    float pv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pv[j] = fmaf(m2, V[8 + j], fmaf(m1, V[4 + j], fmaf(m0, V[j], V[12 + j])));
+    const bool in_front = pv[2] <= -0.000001f;
+
+    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0;
+    if (in_front) {
+        // p_h = p_view @ P ; ndc = p_h / (w + 1e-6) ; pixel centre convention of gauss_render.py:435-436
+        float ph[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            ph[j] = fmaf(pv[3], P[12 + j], fmaf(pv[2], P[8 + j], fmaf(pv[1], P[4 + j], pv[0] * P[j])));
+        const float pw = 1.0f / (ph[3] + 0.000001f);
+        const float mx = ((ph[0] * pw + 1.0f) * (float)p.cam.width - 1.0f) * 0.5f;
+        const float my = ((ph[1] * pw + 1.0f) * (float)p.cam.height - 1.0f) * 0.5f;
+
+        // t = mu @ V[:3,:3] + V[3,:3]
+        const float t0 = fmaf(m2, V[8], fmaf(m1, V[4], m0 * V[0])) + V[12];
+        const float t1 = fmaf(m2, V[9], fmaf(m1, V[5], m0 * V[1])) + V[13];
+        const float tz = fmaf(m2, V[10], fmaf(m1, V[6], m0 * V[2])) + V[14];
+        const float limx = p.cam.tan_fovx * 1.3f, limy = p.cam.tan_fovy * 1.3f;
+        const float tx = fminf(fmaxf(t0 / tz, -limx), limx) * tz;
+        const float ty = fminf(fmaxf(t1 / tz, -limy), limy) * tz;
+        const float itz = 1.0f / tz;
+        const float ja = itz * p.cam.focal_x, jb = -tx / (tz * tz) * p.cam.focal_x;
+        const float jc = itz * p.cam.focal_y, jd = -ty / (tz * tz) * p.cam.focal_y;
+        // W = V[:3,:3]^T  =>  W[r][c] = V[c][r] = V[4*c + r]
+        float M[2][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            M[0][c] = fmaf(jb, V[4 * c + 2], ja * V[4 * c + 0]);
+            M[1][c] = fmaf(jd, V[4 * c + 2], jc * V[4 * c + 1]);
+        }
+        float S[9];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) S[c] = p.cov[9 * i + c];
+        float A[2][3], B[2][3];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                A[r][c] = fmaf(M[r][2], S[6 + c], fmaf(M[r][1], S[3 + c], M[r][0] * S[c]));
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)  // (A @ W^T)[r][c] = sum_k A[r][k] * W[c][k] = sum_k A[r][k] * V[4*k + c]
+                B[r][c] = fmaf(A[r][2], V[8 + c], fmaf(A[r][1], V[4 + c], A[r][0] * V[c]));
+        const float c00 = fmaf(B[0][2], jb, B[0][0] * ja) + 0.3f;
+        const float c01 = fmaf(B[0][2], jd, B[0][1] * jc);
+        const float c10 = fmaf(B[1][2], jb, B[1][0] * ja);
+        const float c11 = fmaf(B[1][2], jd, B[1][1] * jc) + 0.3f;
+
+        const float det = c00 * c11 - c01 * c10;
+        const float mid = 0.5f * (c00 + c11);
+        const float root = sqrtf(fmaxf(mid * mid - det, 0.1f));
+        const float radius = 3.0f * ceilf(sqrtf(fmaxf(mid + root, mid - root)));
+
+        const float idet = 1.0f / det;
+        const float K = -0.72134752044448170368f;  // -0.5 * log2(e): the blend evaluates exp2 directly
+        const float k00 = c11 * idet, k01 = -c01 * idet, k10 = -c10 * idet, k11 = c00 * idet;
+
+        float3 rgb;
+        if (p.shs) {
+            const float dx = m0 - p.cam.campos[0], dy = m1 - p.cam.campos[1], dz = m2 - p.cam.campos[2];
+            const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+            rgb = sh_to_rgb(p.shs + (int64_t)i * 3 * p.sh_stride, p.sh_stride, p.sh_degree,
+                            make_float3(dx * inv, dy * inv, dz * inv));
+        } else {
+            rgb = make_float3(p.colours[3 * i], p.colours[3 * i + 1], p.colours[3 * i + 2]);
+        }
+        q0 = make_float4(mx, my, k00 * K, (k01 + k10) * K);
+        q1 = make_float4(k11 * K, p.opacity[i], rgb.x, rgb.y);
+        q2 = make_float4(rgb.z, pv[2], radius, 1.0f);
+
+        // ---- quadtree membership: flags for nodes that split anyway, exact counts for leaf candidates ----
+        float x0, x1, y0, y1;
+        gaussian_rect(mx, my, radius, p.cam.width, p.cam.height, x0, x1, y0, y1);
+        for (int l = 0; l < p.meta.num_levels; ++l) {
+            const int o1 = (1 << l) - 1;
+            int xlo, xhi, ylo, yhi;
+            axis_range(T.xs + o1, T.xe + o1, l, x0, x1, xlo, xhi);
+            if (xlo > xhi) continue;
+            axis_range(T.ys + o1, T.ye + o1, l, y0, y1, ylo, yhi);
+            if (ylo > yhi) continue;
+            uint32_t* cnt = p.node_cnt + off2(l);
+            for (int iy = ylo; iy <= yhi; ++iy) {
+                if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy)) continue;
+                const int fy = T.yf[o1 + iy];
+                for (int ix = xlo; ix <= xhi; ++ix) {
+                    if (!axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) continue;
+                    uint32_t* c = cnt + (iy << l) + ix;
+                    if ((fy | T.xf[o1 + ix]) & QT_FLAG_BIG) {
+                        if (*(volatile uint32_t*)c == 0u) *c = 1u;  // non-empty flag
+                    } else {
+                        atomicAdd(c, 1u);
+                    }
+                }
+            }
+        }
+    }
+    float4* rec = p.proj + 3 * i;
+    rec[0] = q0; rec[1] = q1; rec[2] = q2;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+struct EmitParams {
+    const float4* proj;
+    int64_t n;
+    int32_t width, height;
+    QtMeta meta;
+    QtTables tab;
+    int32_t n1;
+    const uint8_t* node_state;
+    const int32_t* leaf_of_node;
+    const int32_t* seg_begin;  // instance offset of every leaf
+    uint32_t* cursor;          // per-leaf fill counter (zero-filled by the caller)
+    unsigned long long* keys;  // (depth bits << 32) | Gaussian id
+};
+
+__global__ void __launch_bounds__(256) emit_instances_kernel(const EmitParams p) {
+    extern __shared__ int32_t smem_tab[];
+    const QtTables T = load_tables(p.tab, p.n1, smem_tab);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const float4 q2 = p.proj[3 * i + 2];
+    if (q2.w == 0.0f) return;
+    const float4 q0 = p.proj[3 * i];
+    float x0, x1, y0, y1;
+    gaussian_rect(q0.x, q0.y, q2.z, p.width, p.height, x0, x1, y0, y1);
+    // nearest first: view-space z is negative in front of the camera, sort ascending by -z (gauss_render.py:340-344)
+    const unsigned long long key = ((unsigned long long)__float_as_uint(-q2.y) << 32) | (unsigned long long)(uint32_t)i;
+    for (int l = 0; l < p.meta.num_levels; ++l) {
+        const int o1 = (1 << l) - 1;
+        int xlo, xhi, ylo, yhi;
+        axis_range(T.xs + o1, T.xe + o1, l, x0, x1, xlo, xhi);
+        if (xlo > xhi) continue;
+        axis_range(T.ys + o1, T.ye + o1, l, y0, y1, ylo, yhi);
+        if (ylo > yhi) continue;
+        const int o2 = off2(l);
+        for (int iy = ylo; iy <= yhi; ++iy) {
+            if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy)) continue;
+            for (int ix = xlo; ix <= xhi; ++ix) {
+                if (!axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) continue;
+                const int node = o2 + (iy << l) + ix;
+                if (p.node_state[node] != NODE_LEAF) continue;
+                const int leaf = p.leaf_of_node[node];
+                const uint32_t slot = atomicAdd(p.cursor + leaf, 1u);
+                p.keys[(int64_t)p.seg_begin[leaf] + slot] = key;
+            }
+        }
+    }
+}
+
+QtTables make_tables(const int32_t* tables, int n1) {
+    QtTables t;
+    t.xs = tables; t.xe = tables + n1; t.xf = tables + 2 * n1;
+    t.ys = tables + 3 * n1; t.ye = tables + 4 * n1; t.yf = tables + 5 * n1;
+    return t;
+}
+
+}  // namespace
+
+extern "C" int g2pc_preprocess(const float* xyz, const float* cov, const float* opacity, const float* colours,
+                               const float* shs, int32_t sh_stride, int32_t sh_degree, int64_t n,
+                               const g2pc_camera_t* cam_host, const int32_t* tables, int32_t num_levels,
+                               int32_t max_gaussians_per_tile, void* proj, uint32_t* node_cnt, void* stream) {
+    G2PC_CHECK_ARG(n >= 0, "n < 0");
+    if (n == 0) return G2PC_OK;
+    G2PC_CHECK_ARG(xyz && cov && opacity && cam_host && tables && proj && node_cnt, "null pointer");
+    G2PC_CHECK_ARG((colours != nullptr) != (shs != nullptr), "provide exactly one of colours / shs");
+    G2PC_CHECK_ARG(num_levels >= 1 && num_levels <= G2PC_MAX_LEVELS, "bad num_levels");
+    G2PC_CHECK_ARG(!shs || (sh_degree >= 0 && sh_degree <= 3 && sh_stride >= (sh_degree + 1) * (sh_degree + 1)),
+                   "SH degree must be 0..3 and sh_stride >= (deg+1)^2");
+    PreParams p;
+    p.xyz = xyz; p.cov = cov; p.opacity = opacity; p.colours = colours; p.shs = shs;
+    p.sh_stride = sh_stride; p.sh_degree = sh_degree; p.n = n; p.cam = *cam_host;
+    p.meta.num_levels = num_levels; p.meta.max_gaussians_per_tile = max_gaussians_per_tile;
+    p.meta.width = cam_host->width; p.meta.height = cam_host->height;
+    p.n1 = (1 << num_levels) - 1;
+    p.tab = make_tables(tables, p.n1);
+    p.proj = (float4*)proj; p.node_cnt = node_cnt;
+    const size_t smem = (size_t)6 * p.n1 * sizeof(int32_t);
+    if (smem > 48 * 1024)
+        G2PC_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    preprocess_kernel<<<(unsigned)((n + 255) / 256), 256, smem, (cudaStream_t)stream>>>(p);
+    G2PC_CHECK_LAUNCH();
+    return G2PC_OK;
+}
+
+extern "C" int g2pc_emit_instances(const void* proj, int64_t n, int32_t width, int32_t height, const int32_t* tables,
+                                   int32_t num_levels, const uint8_t* node_state, const int32_t* leaf_of_node,
+                                   const int32_t* seg_begin, uint32_t* cursor, uint64_t* keys, void* stream) {
+    G2PC_CHECK_ARG(n >= 0, "n < 0");
+    if (n == 0) return G2PC_OK;
+    G2PC_CHECK_ARG(proj && tables && node_state && leaf_of_node && seg_begin && cursor && keys, "null pointer");
+    G2PC_CHECK_ARG(num_levels >= 1 && num_levels <= G2PC_MAX_LEVELS, "bad num_levels");
+    EmitParams p;
+    p.proj = (const float4*)proj; p.n = n; p.width = width; p.height = height;
+    p.meta.num_levels = num_levels; p.meta.max_gaussians_per_tile = 0; p.meta.width = width; p.meta.height = height;
+    p.n1 = (1 << num_levels) - 1;
+    p.tab = make_tables(tables, p.n1);
+    p.node_state = node_state; p.leaf_of_node = leaf_of_node; p.seg_begin = seg_begin; p.cursor = cursor;
+    p.keys = (unsigned long long*)keys;
+    const size_t smem = (size_t)6 * p.n1 * sizeof(int32_t);
+    if (smem > 48 * 1024)
+        G2PC_CUDA(cudaFuncSetAttribute(emit_instances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    emit_instances_kernel<<<(unsigned)((n + 255) / 256), 256, smem, (cudaStream_t)stream>>>(p);
+    G2PC_CHECK_LAUNCH();
+    return G2PC_OK;
+}

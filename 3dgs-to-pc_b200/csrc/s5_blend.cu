@@ -1,0 +1,234 @@
+// s5_blend.cu — S5: per-leaf front-to-back blend with per-Gaussian max-contribution tracking; S6: accumulate; image.
+//
+// Reference semantics restated (not copied), renderer_type=python, gauss_render.py:337-402:
+//   every Gaussian of a leaf's depth-ordered list contributes to EVERY pixel of the leaf (no 1/255 cut, no early
+//   termination, no per-pixel radius test):
+//     weight = exp(-0.5 (dx^2 c00 + dy^2 c11 + dx dy c01 + dx dy c10)),  alpha = min(0.99, weight * opacity),
+//     contribution = T * alpha,  T <- T (1 - alpha),  pixel = sum contribution * colour + (1 - sum contribution) * bg
+//   per Gaussian: the largest contribution over the leaf's pixels and the pixel where it occurs; where that beats the
+//   Gaussian's running maximum (strict >, over leaves in BFS order and cameras in call order) the maximum and the
+//   blended colour of that pixel are stored (:371-395).
+//
+// Kernel shape: grid = (slabs, leaves); a CTA owns up to 256 quads (4 consecutive pixels of one row) of one leaf and
+// walks the leaf's sorted list in chunks of 128 records staged in shared memory.  Per thread and Gaussian the
+// row-dependent terms are formed once, then 2 FMA + 1 EX2 + 6 FP32 ops per pixel.  The per-Gaussian maximum is a
+// redux.sync (u32 max of the non-negative float bits) per warp, merged across warps in shared memory and published
+// with ONE 64-bit atomicMax per (CTA, Gaussian): key = (contribution bits << 32) | ~(leaf-pixel index), so ties go to
+// the earliest leaf / lowest pixel, deterministically.  Exact short-cuts only: a warp stops once all its pixels have
+// T below FLT_MIN (every later contribution is then < 1.2e-38).
+#include "colour_common.cuh"
+
+namespace {
+
+constexpr int BT = 256;
+constexpr int CH = 128;
+constexpr unsigned FULLM = 0xffffffffu;
+
+struct BlendParams {
+    const g2pc_leaf_t* leaves;
+    const unsigned long long* keys;
+    const float4* proj;
+    unsigned long long* cam_best;
+    float* leaf_colour;
+    uint32_t* owner;
+    int32_t W, H;
+    float bg;
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+    float r;
+    asm("ex2.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__global__ void __launch_bounds__(BT) blend_kernel(const BlendParams p) {
+    __shared__ float4 s_q0[CH];
+    __shared__ float4 s_q1[CH];
+    __shared__ float s_b[CH];
+    __shared__ uint32_t s_gid[CH];
+    __shared__ unsigned long long s_best[BT / 32][CH];
+
+    const g2pc_leaf_t lf = p.leaves[blockIdx.y];
+    const int qpr = (lf.w + 3) >> 2;
+    const int nquads = qpr * lf.h;
+    const int quad0 = blockIdx.x * BT;
+    if (quad0 >= nquads) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int quad = quad0 + tid;
+    const bool active = quad < nquads;
+    const int row = active ? quad / qpr : 0;
+    const int x0 = active ? (quad - row * qpr) * 4 : 0;
+
+    float T[4], Cr[4], Cg[4], Cb[4], px[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool valid = active && (x0 + i < lf.w);
+        T[i] = valid ? 1.0f : 0.0f;  // T = 0 makes every contribution of a padding pixel exactly 0
+        Cr[i] = Cg[i] = Cb[i] = 0.0f;
+        px[i] = (float)(lf.c0 + x0 + i);
+    }
+    const float py = (float)(lf.r0 + row);
+    const int pix_row = row * lf.w + x0;
+
+    bool warp_done = false;
+    const int cnt = lf.inst_count;
+    for (int base = 0; base < cnt; base += CH) {
+        const int nload = min(CH, cnt - base);
+        if (__syncthreads_and(warp_done ? 1 : 0)) break;  // also orders the previous chunk's smem reads
+        if (tid < nload) {
+            const unsigned long long key = p.keys[(int64_t)lf.inst_begin + base + tid];
+            const uint32_t gid = (uint32_t)key;
+            const float4* rec = p.proj + 3 * (int64_t)gid;
+            s_q0[tid] = __ldg(rec);
+            s_q1[tid] = __ldg(rec + 1);
+            s_b[tid] = __ldg(reinterpret_cast<const float*>(rec + 2));
+            s_gid[tid] = gid;
+        }
+        __syncthreads();
+        if (!warp_done) {
+            for (int j = 0; j < nload; ++j) {
+                const float4 q0 = s_q0[j];
+                const float4 q1 = s_q1[j];
+                const float bl = s_b[j];
+                const float dy = py - q0.y;
+                const float Bq = dy * q0.w;
+                const float Cq = dy * dy * q1.x;
+                float c[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float dx = px[i] - q0.x;
+                    const float e = fmaf(dx, fmaf(dx, q0.z, Bq), Cq);
+                    const float a = fminf(0.99f, ex2f(e) * q1.y);
+                    c[i] = T[i] * a;
+                    Cr[i] = fmaf(c[i], q1.z, Cr[i]);
+                    Cg[i] = fmaf(c[i], q1.w, Cg[i]);
+                    Cb[i] = fmaf(c[i], bl, Cb[i]);
+                    T[i] -= c[i];
+                }
+                const float v = fmaxf(fmaxf(c[0], c[1]), fmaxf(c[2], c[3]));
+                const uint32_t vb = __float_as_uint(v);
+                const uint32_t wm = __reduce_max_sync(FULLM, vb);
+                if (wm != 0u) {
+                    const uint32_t ball = __ballot_sync(FULLM, vb == wm);
+                    if (lane == __ffs(ball) - 1) {
+                        const int i = (c[0] == v) ? 0 : (c[1] == v) ? 1 : (c[2] == v) ? 2 : 3;
+                        s_best[warp][j] = ((unsigned long long)wm << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(pix_row + i));
+                    }
+                } else if (lane == 0) {
+                    s_best[warp][j] = 0ull;
+                }
+            }
+            const float tmax = fmaxf(fmaxf(T[0], T[1]), fmaxf(T[2], T[3]));
+            warp_done = __all_sync(FULLM, tmax < 1.17549435e-38f);
+        } else {
+            for (int j = lane; j < nload; j += 32) s_best[warp][j] = 0ull;
+        }
+        __syncthreads();
+        if (tid < nload) {
+            unsigned long long best = s_best[0][tid];
+#pragma unroll
+            for (int w = 1; w < BT / 32; ++w) {
+                const unsigned long long o = s_best[w][tid];
+                best = o > best ? o : best;
+            }
+            if ((best >> 32) != 0ull) {
+                // leaf-local pixel -> index into the concatenated leaf-colour buffer (earlier leaf => smaller index)
+                const uint32_t pix = 0xFFFFFFFFu - (uint32_t)best;
+                const unsigned long long packed = (best & 0xFFFFFFFF00000000ull) |
+                                                  (unsigned long long)(0xFFFFFFFFu - (uint32_t)(lf.pix_offset + pix));
+                atomicMax(p.cam_best + s_gid[tid], packed);
+            }
+        }
+    }
+    // final pixel colours: sum + (1 - sum of contributions) * bg; the second factor equals the final T
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (x0 + i < lf.w) {
+                const int64_t lp = (int64_t)lf.pix_offset + pix_row + i;
+                float* o = p.leaf_colour + 3 * lp;
+                o[0] = fmaf(T[i], p.bg, Cr[i]);
+                o[1] = fmaf(T[i], p.bg, Cg[i]);
+                o[2] = fmaf(T[i], p.bg, Cb[i]);
+                // overlapping leaves: the later BFS entry wins the image pixel (gauss_render.py:369)
+                atomicMax(p.owner + (int64_t)(lf.r0 + row) * p.W + (lf.c0 + x0 + i), (uint32_t)lp + 1u);
+            }
+        }
+    }
+}
+
+// S6: fold one camera's per-Gaussian winners into the running maxima (strict >, earlier camera wins ties) and fetch
+// the blended colour of the winning pixel (gauss_render.py:387-395); clears cam_best for the next camera.
+__global__ void __launch_bounds__(256) accumulate_kernel(unsigned long long* __restrict__ cam_best,
+                                                         const float* __restrict__ leaf_colour, int64_t n,
+                                                         float* __restrict__ max_contrib, float* __restrict__ colours) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const unsigned long long b = cam_best[g];
+    if (b == 0ull) return;
+    cam_best[g] = 0ull;
+    const float v = __uint_as_float((uint32_t)(b >> 32));
+    if (v > max_contrib[g]) {
+        max_contrib[g] = v;
+        const int64_t idx = (int64_t)(0xFFFFFFFFu - (uint32_t)b);
+        colours[3 * g] = leaf_colour[3 * idx];
+        colours[3 * g + 1] = leaf_colour[3 * idx + 1];
+        colours[3 * g + 2] = leaf_colour[3 * idx + 2];
+    }
+}
+
+// image = leaf colours where a leaf covers the pixel, else background; flipped left-right (gauss_render.py:402)
+__global__ void __launch_bounds__(256) compose_kernel(uint32_t* __restrict__ owner, const float* __restrict__ leaf_colour,
+                                                      int W, int H, float bg, float* __restrict__ image) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)W * H) return;
+    const int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
+    const uint32_t o = owner[i];
+    owner[i] = 0u;
+    float r = bg, g = bg, b = bg;
+    if (o) { const float* c = leaf_colour + 3 * (int64_t)(o - 1u); r = c[0]; g = c[1]; b = c[2]; }
+    float* out = image + 3 * ((int64_t)y * W + (W - 1 - x));
+    out[0] = r; out[1] = g; out[2] = b;
+}
+
+}  // namespace
+
+extern "C" int g2pc_blend(const g2pc_leaf_t* leaves, int32_t num_leaves, int32_t max_leaf_pixels_quads,
+                          const uint64_t* keys, const void* proj, uint64_t* cam_best, float* leaf_colour,
+                          uint32_t* owner, int32_t width, int32_t height, float background, void* stream) {
+    G2PC_CHECK_ARG(num_leaves >= 0, "negative size");
+    if (num_leaves == 0) return G2PC_OK;
+    G2PC_CHECK_ARG(leaves && keys && proj && cam_best && leaf_colour && owner, "null pointer");
+    G2PC_CHECK_ARG(max_leaf_pixels_quads >= 1, "max_leaf_pixels_quads < 1");
+    BlendParams p;
+    p.leaves = leaves; p.keys = (const unsigned long long*)keys; p.proj = (const float4*)proj;
+    p.cam_best = (unsigned long long*)cam_best; p.leaf_colour = leaf_colour; p.owner = owner;
+    p.W = width; p.H = height; p.bg = background;
+    const unsigned slabs = (unsigned)((max_leaf_pixels_quads + BT - 1) / BT);
+    G2PC_CHECK_ARG(num_leaves <= 65535, "too many leaves for one launch");
+    blend_kernel<<<dim3(slabs, (unsigned)num_leaves), BT, 0, (cudaStream_t)stream>>>(p);
+    G2PC_CHECK_LAUNCH();
+    return G2PC_OK;
+}
+
+extern "C" int g2pc_accumulate(uint64_t* cam_best, const float* leaf_colour, int64_t n, float* max_contrib,
+                               float* colours, void* stream) {
+    G2PC_CHECK_ARG(n >= 0, "n < 0");
+    if (n == 0) return G2PC_OK;
+    G2PC_CHECK_ARG(cam_best && leaf_colour && max_contrib && colours, "null pointer");
+    accumulate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (unsigned long long*)cam_best, leaf_colour, n, max_contrib, colours);
+    G2PC_CHECK_LAUNCH();
+    return G2PC_OK;
+}
+
+extern "C" int g2pc_compose_image(uint32_t* owner, const float* leaf_colour, int32_t width, int32_t height,
+                                  float background, float* image, void* stream) {
+    G2PC_CHECK_ARG(width > 0 && height > 0, "bad image size");
+    G2PC_CHECK_ARG(owner && leaf_colour && image, "null pointer");
+    const int64_t n = (int64_t)width * height;
+    compose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(owner, leaf_colour, width, height,
+                                                                                    background, image);
+    G2PC_CHECK_LAUNCH();
+    return G2PC_OK;
+}

@@ -33,7 +33,30 @@ SIGNATURES = {
     "g2pc_sample_emit": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _i32, _u64, _u32, _c_void_p,
                           _c_void_p, _c_void_p, ctypes.c_int, _i64, _c_void_p], ctypes.c_int),
     "g2pc_dump_eps": ([_c_void_p, _i64, _i32, _i32, _u64, _u32, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_preprocess": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i32, _i32, _i64, _c_void_p, _c_void_p,
+                         _i32, _i32, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_build_tree": ([_c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i32, _c_void_p,
+                         _c_void_p], ctypes.c_int),
+    "g2pc_emit_instances": ([_c_void_p, _i64, _i32, _i32, _c_void_p, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                             _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_sort_workspace_bytes": ([_i64, _i32], ctypes.c_int64),
+    "g2pc_sort_leaves": ([_c_void_p, _c_void_p, _i64, _i32, _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p],
+                         ctypes.c_int),
+    "g2pc_blend": ([_c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i32, _i32, _f32,
+                    _c_void_p], ctypes.c_int),
+    "g2pc_accumulate": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_compose_image": ([_c_void_p, _c_void_p, _i32, _i32, _f32, _c_void_p, _c_void_p], ctypes.c_int),
 }
+
+
+class Camera(ctypes.Structure):
+    """g2pc_camera_t"""
+    _fields_ = [("view", _f32 * 16), ("proj", _f32 * 16), ("campos", _f32 * 3), ("tan_fovx", _f32),
+                ("tan_fovy", _f32), ("focal_x", _f32), ("focal_y", _f32), ("width", _i32), ("height", _i32)]
+
+
+HDR_NUM_LEAVES, HDR_TOTAL_INST, HDR_TOTAL_PIX, HDR_NEED_DEEPER, HDR_LEAF_OVERFLOW, HDR_WORDS = 0, 1, 2, 3, 4, 8
+LEAF_WORDS = 8  # g2pc_leaf_t = 8 x int32
 
 _lib = None
 
