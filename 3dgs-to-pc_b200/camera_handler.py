@@ -37,7 +37,11 @@ def getProjectionMatrix(znear, zfar, fovX, fovY):
 
 class Camera():
     """Pinhole camera of the python renderer (camera_handler.py:36-50): OpenGL c2w (looks down -z), row-vector
-    view matrix world_view_transform = inv(c2w)^T, znear 10, zfar 100."""
+    view matrix world_view_transform = inv(c2w)^T, znear 10, zfar 100.
+
+    The 4x4 algebra runs on the host in float32 (the kernels take the matrices by value); the tensor attributes of the
+    reference (world_view_transform, projection_matrix, camera_center, full_proj_transform) are exposed on c2w's
+    device on first access."""
 
     def __init__(self, width, height, focal_x, focal_y, c2w, znear=10, zfar=100):
         self.znear = znear
@@ -48,12 +52,27 @@ class Camera():
         self.FoVy = focal2fov(self.focal_y, height)
         self.image_width = int(width)
         self.image_height = int(height)
-        self.world_view_transform = torch.linalg.inv(c2w).permute(1, 0)
         self.c2w = c2w
-        self.projection_matrix = getProjectionMatrix(znear=self.znear, zfar=self.zfar, fovX=self.FoVx,
-                                                     fovY=self.FoVy).transpose(0, 1).to(c2w.device)
-        self.camera_center = self.world_view_transform.inverse()[3, :3]
-        self.full_proj_transform = self.world_view_transform @ self.projection_matrix
+        host = c2w.detach().to("cpu", torch.float32)
+        self._host = {}
+        self._host["world_view_transform"] = torch.linalg.inv(host).permute(1, 0).contiguous()
+        self._host["projection_matrix"] = getProjectionMatrix(znear=self.znear, zfar=self.zfar, fovX=self.FoVx,
+                                                               fovY=self.FoVy).transpose(0, 1).contiguous()
+        self._host["camera_center"] = self._host["world_view_transform"].inverse()[3, :3].contiguous()
+        self._host["full_proj_transform"] = self._host["world_view_transform"] @ self._host["projection_matrix"]
+        self._dev = {}
+
+    def host(self, name):
+        return self._host[name]
+
+    def __getattr__(self, name):
+        h = self.__dict__.get("_host", {})
+        if name in h:
+            d = self.__dict__["_dev"]
+            if name not in d:
+                d[name] = h[name].to(self.__dict__["c2w"].device)
+            return d[name]
+        raise AttributeError(name)
 
 
 def get_camera(renderer_type, transform, cam_intrinsic, colour_resolution=None, sh_degree=3, white_bkgd=True, mask=None):

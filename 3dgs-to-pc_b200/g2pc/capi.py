@@ -84,6 +84,29 @@ def load(path=None):
     return lib
 
 
+# ---- launch accounting (bench.py reads these) -------------------------------------------------------------------
+LAUNCHES = 0      # number of g2pc kernel entry points invoked since the last reset
+TIMING = None     # None, or {entry point name: [(start_event, end_event), ...]} to time launches with CUDA events
+_NOT_KERNELS = {"g2pc_version", "g2pc_last_error", "g2pc_sort_workspace_bytes"}
+
+
+def call(name, *args):
+    """Invoke entry point `name` (must be declared in SIGNATURES), check its status, count it, and — when TIMING is a
+    dict — bracket it with CUDA events on the current stream."""
+    global LAUNCHES
+    fn = getattr(load(), name)
+    if TIMING is not None and name in TIMING:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        status = fn(*args)
+        b.record()
+        TIMING[name].append((a, b))
+    else:
+        status = fn(*args)
+    LAUNCHES += 1
+    check(status, name)
+
+
 def check(status, what):
     if status != 0:
         msg = load().g2pc_last_error()

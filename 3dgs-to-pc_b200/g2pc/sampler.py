@@ -167,11 +167,10 @@ def run_plan(plan, xyz, cov, colours, normals, perm, num_attempts, std, seed, ca
     tile_totals = torch.zeros((max(nt, 1) * A,), dtype=torch.int32, device=dev)
     status = torch.zeros((capi.ST_WORDS,), dtype=torch.int32, device=dev)
 
-    capi.check(lib.g2pc_sample_count(
-        capi.ptr(xyz), capi.ptr(cov), capi.ptr(colours), capi.dtype_code(colours), capi.ptr(normals),
+    capi.call("g2pc_sample_count", capi.ptr(xyz), capi.ptr(cov), capi.ptr(colours), capi.dtype_code(colours), capi.ptr(normals),
         capi.ptr(perm), int(gid_offset), n, capi.ptr(tiles_d), nt, int(num_attempts), A, float(std),
         int(cull_mode), int(seed) & 0xFFFFFFFFFFFFFFFF, int(call_id) & 0xFFFFFFFF, capi.ptr(records), capi.ptr(xl),
-        capi.ptr(tile_totals), capi.ptr(status), st), "g2pc_sample_count")
+        capi.ptr(tile_totals), capi.ptr(status), st)
 
     lens = torch.cat([tile_totals[: nt * A].to(torch.int64), centre_d])[src_d]
     unit_base = torch.zeros((nu + 1,), dtype=torch.int64, device=dev)
@@ -183,10 +182,9 @@ def run_plan(plan, xyz, cov, colours, normals, perm, num_attempts, std, seed, ca
     rgb = torch.empty((max(cap, 1), 3), dtype=out_dtype, device=dev)
     nrm = torch.empty((max(cap, 1), 3), dtype=out_dtype, device=dev) if (want_normals and normals is not None) else None
 
-    capi.check(lib.g2pc_sample_emit(
-        capi.ptr(records), capi.ptr(xl), n, capi.ptr(units_d), capi.ptr(unit_base), nu,
+    capi.call("g2pc_sample_emit", capi.ptr(records), capi.ptr(xl), n, capi.ptr(units_d), capi.ptr(unit_base), nu,
         int(seed) & 0xFFFFFFFFFFFFFFFF, int(call_id) & 0xFFFFFFFF, capi.ptr(pts), capi.ptr(rgb), capi.ptr(nrm),
-        capi.dtype_code(rgb), cap, st), "g2pc_sample_emit")
+        capi.dtype_code(rgb), cap, st)
     return pts, rgb, nrm, unit_base[nu], status, (records, xl, tile_totals, unit_base)
 
 
@@ -197,7 +195,7 @@ def dump_eps(gids, k, attempt, seed, call_id=0):
     capi.require_cuda(gids)
     gids = gids.to(torch.int64).contiguous()
     eps = torch.empty((k, gids.shape[0], 3), dtype=torch.float32, device=gids.device)
-    capi.check(lib.g2pc_dump_eps(capi.ptr(gids), gids.shape[0], int(k), int(attempt),
+    capi.call("g2pc_dump_eps", capi.ptr(gids), gids.shape[0], int(k), int(attempt),
                                  int(seed) & 0xFFFFFFFFFFFFFFFF, int(call_id) & 0xFFFFFFFF, capi.ptr(eps),
-                                 capi.stream_ptr(gids.device)), "g2pc_dump_eps")
+                                 capi.stream_ptr(gids.device))
     return eps

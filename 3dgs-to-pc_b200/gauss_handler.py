@@ -63,9 +63,8 @@ def build_covariance_from_scaling_rotation(scaling, scaling_modifier, rotation):
     if scaling.shape[1] != 3 or rotation.shape != (n, 4):
         raise ValueError("scaling must be (N,3) and rotation (N,4)")
     cov = torch.empty((n, 3, 3), dtype=torch.float32, device=scaling.device)
-    capi.check(lib.g2pc_cov_build(capi.ptr(scaling), capi.ptr(rotation), capi.dtype_code(scaling),
-                                  float(scaling_modifier), n, capi.ptr(cov), capi.stream_ptr(scaling.device)),
-               "g2pc_cov_build")
+    capi.call("g2pc_cov_build", capi.ptr(scaling), capi.ptr(rotation), capi.dtype_code(scaling),
+                                  float(scaling_modifier), n, capi.ptr(cov), capi.stream_ptr(scaling.device))
     return cov
 
 
@@ -75,8 +74,7 @@ def eigvals_sym3(covariances):
     capi.require_cuda(covariances)
     c = covariances.to(torch.float32).contiguous()
     ev = torch.empty((c.shape[0], 3), dtype=torch.float32, device=c.device)
-    capi.check(lib.g2pc_eigvals_sym3(capi.ptr(c), c.shape[0], capi.ptr(ev), capi.stream_ptr(c.device)),
-               "g2pc_eigvals_sym3")
+    capi.call("g2pc_eigvals_sym3", capi.ptr(c), c.shape[0], capi.ptr(ev), capi.stream_ptr(c.device))
     return ev
 
 
@@ -114,8 +112,8 @@ class Gaussians():
             s, r = s.to(torch.float64), r.to(torch.float64)
         n = s.shape[0]
         normals = torch.empty((n, 3), dtype=torch.float32, device=s.device)
-        capi.check(lib.g2pc_normals(capi.ptr(s), capi.ptr(r), capi.dtype_code(s), n, capi.ptr(normals),
-                                    capi.stream_ptr(s.device)), "g2pc_normals")
+        capi.call("g2pc_normals", capi.ptr(s), capi.ptr(r), capi.dtype_code(s), n, capi.ptr(normals),
+                                    capi.stream_ptr(s.device))
         self.normals = normals
 
     def non_posdef_covariances(self, covariances, epsilon: float = 1e-10):

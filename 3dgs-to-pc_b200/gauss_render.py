@@ -125,9 +125,13 @@ class GaussPythonRenderer():
     @staticmethod
     def _camera_struct(camera):
         c = capi.Camera()
-        V = camera.world_view_transform.detach().to("cpu", torch.float32).contiguous().reshape(-1).tolist()
-        P = camera.projection_matrix.detach().to("cpu", torch.float32).contiguous().reshape(-1).tolist()
-        pos = camera.camera_center.detach().to("cpu", torch.float32).reshape(-1).tolist()
+        if hasattr(camera, "host"):  # matrices already on the host (camera_handler.Camera)
+            get = camera.host
+        else:
+            get = lambda k: getattr(camera, k).detach().to("cpu", torch.float32)
+        V = get("world_view_transform").contiguous().reshape(-1).tolist()
+        P = get("projection_matrix").contiguous().reshape(-1).tolist()
+        pos = get("camera_center").reshape(-1).tolist()
         for i in range(16):
             c.view[i] = V[i]
             c.proj[i] = P[i]
@@ -161,16 +165,14 @@ class GaussPythonRenderer():
             qt = t["qt"]
             t["node_cnt"].zero_()
             t["leaf_of_node"].fill_(-1)
-            capi.check(lib.g2pc_preprocess(
-                capi.ptr(self.means3D), capi.ptr(self.cov3d), capi.ptr(self.opacity),
+            capi.call("g2pc_preprocess", capi.ptr(self.means3D), capi.ptr(self.cov3d), capi.ptr(self.opacity),
                 capi.ptr(self._colour_f32) if self.shs is None else None,
                 capi.ptr(self.shs), int(self.shs.shape[-1]) if self.shs is not None else 0, self.sh_degree, n,
                 ctypes.byref(cam), capi.ptr(t["tables"]), qt.num_levels, qt.max_gaussians_per_tile,
-                capi.ptr(self._proj), capi.ptr(t["node_cnt"]), st), "g2pc_preprocess")
-            capi.check(lib.g2pc_build_tree(
-                capi.ptr(t["tables"]), qt.num_levels, qt.max_gaussians_per_tile, capi.ptr(t["node_cnt"]),
+                capi.ptr(self._proj), capi.ptr(t["node_cnt"]), st)
+            capi.call("g2pc_build_tree", capi.ptr(t["tables"]), qt.num_levels, qt.max_gaussians_per_tile, capi.ptr(t["node_cnt"]),
                 capi.ptr(t["node_state"]), capi.ptr(t["leaf_of_node"]), capi.ptr(t["leaves"]),
-                capi.ptr(t["seg_begin"]), qt.nodes_2d, capi.ptr(t["header"]), st), "g2pc_build_tree")
+                capi.ptr(t["seg_begin"]), qt.nodes_2d, capi.ptr(t["header"]), st)
             self._hdr_host.copy_(t["header"], non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()  # the one host read per camera (32 bytes)
             hdr = self._hdr_host.tolist()
@@ -191,29 +193,27 @@ class GaussPythonRenderer():
             keys_alt = self._grow("_keys_alt", total_inst, torch.int64)
             leaf_colour = self._grow("_leaf_colour", total_pix * 3, torch.float32)
             t["cursor"][:num_leaves].zero_()
-            capi.check(lib.g2pc_emit_instances(
-                capi.ptr(self._proj), n, W, H, capi.ptr(t["tables"]), qt.num_levels, capi.ptr(t["node_state"]),
-                capi.ptr(t["leaf_of_node"]), capi.ptr(t["seg_begin"]), capi.ptr(t["cursor"]), capi.ptr(keys), st),
-                "g2pc_emit_instances")
+            capi.call("g2pc_emit_instances", capi.ptr(self._proj), n, W, H, capi.ptr(t["tables"]), qt.num_levels, capi.ptr(t["node_state"]),
+                capi.ptr(t["leaf_of_node"]), capi.ptr(t["seg_begin"]), capi.ptr(t["cursor"]), capi.ptr(keys), st)
             ws_bytes = lib.g2pc_sort_workspace_bytes(total_inst, num_leaves)
             if ws_bytes < 0:
                 raise capi.G2pcError("cub workspace query failed")
             ws = self._grow("_sort_ws", max(ws_bytes, 1), torch.uint8)
             in_alt = ctypes.c_int32(0)
-            capi.check(lib.g2pc_sort_leaves(capi.ptr(keys), capi.ptr(keys_alt), total_inst, num_leaves,
+            capi.call("g2pc_sort_leaves", capi.ptr(keys), capi.ptr(keys_alt), total_inst, num_leaves,
                                             capi.ptr(t["seg_begin"]), capi.ptr(ws), ws.numel(), ctypes.byref(in_alt),
-                                            st), "g2pc_sort_leaves")
+                                            st)
             sorted_keys = keys_alt if in_alt.value else keys
             self._last_sorted_keys = sorted_keys
-            capi.check(lib.g2pc_blend(capi.ptr(t["leaves"]), num_leaves, t["max_quads"], capi.ptr(sorted_keys),
+            capi.call("g2pc_blend", capi.ptr(t["leaves"]), num_leaves, t["max_quads"], capi.ptr(sorted_keys),
                                       capi.ptr(self._proj), capi.ptr(self._cam_best), capi.ptr(leaf_colour),
-                                      capi.ptr(t["owner"]), W, H, bg, st), "g2pc_blend")
-            capi.check(lib.g2pc_accumulate(capi.ptr(self._cam_best), capi.ptr(leaf_colour), n,
+                                      capi.ptr(t["owner"]), W, H, bg, st)
+            capi.call("g2pc_accumulate", capi.ptr(self._cam_best), capi.ptr(leaf_colour), n,
                                            capi.ptr(self.gaussian_max_contribution), capi.ptr(self.gaussian_colours),
-                                           st), "g2pc_accumulate")
+                                           st)
             if self.compose_image:
-                capi.check(lib.g2pc_compose_image(capi.ptr(t["owner"]), capi.ptr(leaf_colour), W, H, bg,
-                                                  capi.ptr(t["image"]), st), "g2pc_compose_image")
+                capi.call("g2pc_compose_image", capi.ptr(t["owner"]), capi.ptr(leaf_colour), W, H, bg,
+                                                  capi.ptr(t["image"]), st)
             else:
                 t["owner"].zero_()
         elif self.compose_image:

@@ -19,6 +19,7 @@ from gauss_render import get_renderer
 from camera_handler import get_camera
 from g2pc import capi, config, sampler
 
+LAST_SAMPLE_STATS = {}
 COLOR_QUALITY_OPTIONS = {"tiny": 180, "low": 360, "medium": 720, "high": 1280, "ultra": 1920, "original": None}
 
 
@@ -196,6 +197,8 @@ def sample_points_per_gaussian(xyz, covariances, colours, normals, points_per_ga
     order = torch.sort(bin_of, stable=True).indices
     n_used = int(sum(c for (_, _, _, c) in bins))
     perm = order[:n_used].to(torch.int32)
+    global LAST_SAMPLE_STATS
+    LAST_SAMPLE_STATS = {"n_active": n_used, "bins": len(bins)}
 
     A = min(int(num_sample_attempts), config.MAX_ATTEMPTS_STORED)
     plan = sampler.SamplePlan([(n - 1, count) for (_, _, n, count) in bins], A, include_centres=True)
@@ -218,6 +221,7 @@ def convert_3dgs_to_pc(input_path, transform_path, mask_path, pointcloud_setting
 
     s = pointcloud_settings
     say = (lambda *a: None) if s.quiet else print
+    transforms, intrinsics, mask_images = None, None, None
 
     if transform_path is not None:
         say("Loading Camera Poses\n")
@@ -232,6 +236,17 @@ def convert_3dgs_to_pc(input_path, transform_path, mask_path, pointcloud_setting
 
     say("Loading Gaussians from File\n")
     xyz, scales, rots, colours, opacities, shs = load_gaussians(input_path, max_sh_degree=s.max_sh_degree)
+    return convert_gaussians_to_pc(xyz, scales, rots, colours, opacities, shs, transforms, intrinsics, mask_images, s)
+
+
+def convert_gaussians_to_pc(xyz, scales, rots, colours, opacities, shs, transforms, intrinsics, mask_images,
+                            pointcloud_settings, render_shs=False):
+    """The device-resident part of convert_3dgs_to_pc (gauss_to_pc.py:414-601): everything between the loaders and the
+    PLY writer.  transforms: {name: 4x4 c2w (nested list / tensor)} or None; intrinsics: {name: [w, h, fx, fy]}.
+    render_shs=True evaluates the SH colour per camera inside the colour stage (the reference's CLI never passes the SH
+    coefficients to its renderer, gauss_to_pc.py:429-432; get_renderer accepts them)."""
+    s = pointcloud_settings
+    say = (lambda *a: None) if s.quiet else print
 
     gaussians = Gaussians(xyz, scales, rots, colours, opacities, shs=shs)
 
@@ -246,17 +261,21 @@ def convert_3dgs_to_pc(input_path, transform_path, mask_path, pointcloud_setting
         want_surface = True if (s.surface_distance_std is not None or s.generate_mesh) else False
         gaussian_renderer = get_renderer(s.renderer_type, gaussians.xyz, torch.unsqueeze(torch.clone(gaussians.opacities), 1),
                                          gaussians.colours, gaussians.covariances,
+                                         shs=gaussians.shs if render_shs else None,
                                          visible_gaussian_threshold=s.visibility_threshold,
                                          surface_distance_std=s.surface_distance_std,
                                          calculate_surface_distance=want_surface)
+        if not getattr(s, "keep_images", True) and hasattr(gaussian_renderer, "compose_image"):
+            gaussian_renderer.compose_image = False
 
-        if transform_path is None:
+        if transforms is None:
             raise Exception("Transforms are required to render colours")
 
         for img_name, transform in transforms.items():
-            transform = torch.tensor(list(transform), device=s.device)
+            # the 4x4 pose stays on the host: the camera matrices are kernel arguments, not device data
+            transform = torch.as_tensor(transform, dtype=torch.float32) if not torch.is_tensor(transform) else transform
             mask = None
-            if mask_path is not None and img_name in mask_images.keys():
+            if mask_images is not None and img_name in mask_images.keys():
                 mask = mask_images[img_name].to(s.device)
             camera = get_camera(s.renderer_type, transform, intrinsics[img_name], colour_resolution=s.colour_resolution,
                                 sh_degree=s.max_sh_degree, white_bkgd=True, mask=mask)
@@ -292,7 +311,7 @@ def convert_3dgs_to_pc(input_path, transform_path, mask_path, pointcloud_setting
 
         del gaussian_renderer
     else:
-        gaussians.colours *= 255
+        gaussians.colours = gaussians.colours * 255
         say("Skipping Rendering Gaussian Colours")
 
     say("\nEnsuring Gaussians are Positive Semidefinite")
@@ -328,9 +347,6 @@ def convert_3dgs_to_pc(input_path, transform_path, mask_path, pointcloud_setting
                                                        contributions=total_gaussian_contributions[surface_gaussian_idxs],
                                                        device=s.device, quiet=s.quiet)
         surface_point_cloud = PointCloudData(points=points, colours=colours, normals=normals)
-
-    torch.cuda.empty_cache()
-    gc.collect()
 
     return total_point_cloud, surface_point_cloud
 

@@ -165,11 +165,34 @@ def blend_leaf(r0, c0, w, h, mx, my, conic, opacity, colour, white_bkgd=True):
     return col, contrib
 
 
+def blend_leaf_dense(r0, c0, w, h, mx, my, conic, opacity, colour, white_bkgd=True):
+    """Same leaf blend as blend_leaf but with the reference's dense (pixels x Gaussians) tensor formulation
+    (gauss_render.py:353-385: broadcast dx, exp, clip, exclusive cumprod, reductions) on torch-CPU, multi-threaded —
+    the form the reference's own CPU run takes; used as the CPU baseline.  Returns (tile_colour, best, argbest)."""
+    ys, xs = torch.meshgrid(torch.arange(r0, r0 + h), torch.arange(c0, c0 + w), indexing="ij")
+    coord = torch.stack([xs.reshape(-1), ys.reshape(-1)], dim=-1)  # int64 (x, y) per pixel, row-major
+    m2 = torch.as_tensor(np.stack([mx, my], axis=-1))
+    con = torch.as_tensor(conic)
+    op = torch.as_tensor(opacity).reshape(-1, 1)
+    colr = torch.as_tensor(colour)
+    dx = coord[:, None, :] - m2[None, :]
+    wgt = torch.exp(-0.5 * (dx[:, :, 0] ** 2 * con[:, 0, 0] + dx[:, :, 1] ** 2 * con[:, 1, 1]
+                            + dx[:, :, 0] * dx[:, :, 1] * con[:, 0, 1] + dx[:, :, 0] * dx[:, :, 1] * con[:, 1, 0]))
+    alpha = (wgt[..., None] * op[None]).clip(max=0.99)
+    T = torch.cat([torch.ones_like(alpha[:, :1]), 1 - alpha[:, :-1]], dim=1).cumprod(dim=1)
+    acc = (alpha * T).sum(dim=1)
+    bg = 1 if white_bkgd else 0
+    col = (T * alpha * colr[None]).sum(dim=1) + (1 - acc) * bg
+    best = torch.max((T * alpha).squeeze(2), 0)
+    return col.numpy(), best[0].numpy(), best[1].numpy()
+
+
 class PythonRendererOracle:
     """Restatement of GaussPythonRenderer (gauss_render.py:210-465) with pinned tile parameters."""
 
     def __init__(self, means3D, opacity, colour, cov3d, max_tile_size=60, max_gaussians_per_tile=60000, shs=None,
-                 sh_degree=0):
+                 sh_degree=0, dense=False):
+        self.dense = dense
         self.means3D = torch.as_tensor(means3D, dtype=torch.float32)
         self.opacity = torch.as_tensor(opacity, dtype=torch.float32).reshape(-1)
         self.colour = None if colour is None else torch.as_tensor(colour, dtype=torch.float64)
@@ -209,10 +232,13 @@ class PythonRendererOracle:
             order = np.lexsort((members, -depth[members]))
             ids = members[order]
             conic = torch.inverse(cov2d[ids]).numpy()
-            col, contrib = blend_leaf(r0, c0, w, h, mx[ids], my[ids], conic, opacity[ids], colour[ids])
+            if self.dense:
+                col, best, arg = blend_leaf_dense(r0, c0, w, h, mx[ids], my[ids], conic, opacity[ids], colour[ids])
+            else:
+                col, contrib = blend_leaf(r0, c0, w, h, mx[ids], my[ids], conic, opacity[ids], colour[ids])
+                best = contrib.max(axis=0)
+                arg = contrib.argmax(axis=0)
             image[r0:r0 + h, c0:c0 + w] = col.reshape(h, w, 3).astype(np.float32)
-            best = contrib.max(axis=0)
-            arg = contrib.argmax(axis=0)
             gl = vis[ids]
             upd = best > self.gaussian_max_contribution[gl]
             self.gaussian_max_contribution[gl[upd]] = best[upd]
