@@ -7,8 +7,10 @@
 //   gauss_render.py:349      conic = inverse(cov2d)
 //   gauss_render.py:43-99    eval_sh (+0.5, clamp >= 0 as forward.cu:65-72) when SH coefficients are supplied
 //   gauss_render.py:301-319  tile membership: min(rect_max, tile_max) > max(rect_min, tile_min), strict, fp32
-// One thread per Gaussian.  Membership is evaluated by range queries on the per-level interval tables
-// (g2pc/quadtree.py) instead of testing every tile against every Gaussian.
+// One thread per Gaussian, 2048 Gaussians per CTA.  Membership is evaluated by range queries on the per-level interval
+// tables (g2pc/quadtree.py) instead of testing every tile against every Gaussian; the per-node overlap counts are
+// accumulated in a shared-memory histogram and flushed once per CTA (a few thousand global atomics per CTA instead
+// of ~7 per Gaussian on ~1000 hot addresses).
 #include "colour_common.cuh"
 
 namespace {
@@ -27,12 +29,17 @@ struct PreParams {
     int32_t n1;  // entries per 1-D table array
     float4* proj;
     uint32_t* node_cnt;
+    uint32_t* depth_key;  // bits(-z_view) for Gaussians in front of the camera, 0xFFFFFFFF otherwise
+    uint32_t* touched;    // number of leaf-candidate nodes the Gaussian overlaps (upper bound of its instances)
+    int32_t nodes_2d;     // histogram entries (0: no shared-memory histogram, global atomics)
 };
+
+constexpr int PRE_PER_CTA = 2048;
 
 __device__ __forceinline__ int off2(int l) { return ((1 << (2 * l)) - 1) / 3; }
 
 __device__ __forceinline__ float3 sh_to_rgb(const float* __restrict__ sh, int stride, int deg, float3 d) {
-    // sh: 3 channels x stride coefficients (channel-major)
+    // sh: 3 channels x stride coefficients (channel-major).  16-byte loads when the row is 16-byte aligned.
     const float C0 = 0.28209479177387814f, C1 = 0.4886025119029199f;
     const float C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f,
                          0.5462742152960396f};
@@ -41,9 +48,24 @@ __device__ __forceinline__ float3 sh_to_rgb(const float* __restrict__ sh, int st
     float out[3];
     const float x = d.x, y = d.y, z = d.z;
     const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    const int ncoef = (deg + 1) * (deg + 1);
+    const bool vec = ((stride & 3) == 0) && ((((uintptr_t)sh) & 15) == 0);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const float* s = sh + c * stride;
+        float s[16];
+        if (vec) {
+            const float4* s4 = reinterpret_cast<const float4*>(sh + c * stride);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (4 * q < ncoef) {
+                    const float4 v = __ldg(s4 + q);
+                    s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) if (k < ncoef) s[k] = sh[c * stride + k];
+        }
         float r = C0 * s[0];
         if (deg > 0) {
             r = r - C1 * y * s[1] + C1 * z * s[2] - C1 * x * s[3];
@@ -65,9 +87,14 @@ __device__ __forceinline__ float3 sh_to_rgb(const float* __restrict__ sh, int st
 
 __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
     extern __shared__ int32_t smem_tab[];
-    const QtTables T = load_tables(p.tab, p.n1, smem_tab);
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.n) return;
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_tab + 6 * p.n1);
+    for (int k = threadIdx.x; k < p.nodes_2d; k += blockDim.x) s_hist[k] = 0u;
+    const QtTables T = load_tables(p.tab, p.n1, smem_tab);  // ends with __syncthreads()
+    const bool use_hist = p.nodes_2d > 0;
+    const int64_t cta_base = (int64_t)blockIdx.x * PRE_PER_CTA;
+  for (int it = 0; it < PRE_PER_CTA / 256; ++it) {
+    const int64_t i = cta_base + it * 256 + threadIdx.x;
+    if (i >= p.n) break;
 
     const float* V = p.cam.view;
     const float* P = p.cam.proj;
@@ -80,6 +107,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
     const bool in_front = pv[2] <= -0.000001f;
 
     float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0;
+    uint32_t n_touched = 0;
     if (in_front) {
         // p_h = p_view @ P ; ndc = p_h / (w + 1e-6) ; pixel centre convention of gauss_render.py:435-436
         float ph[4];
@@ -145,7 +173,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
             rgb = make_float3(p.colours[3 * i], p.colours[3 * i + 1], p.colours[3 * i + 2]);
         }
         q0 = make_float4(mx, my, k00 * K, (k01 + k10) * K);
-        q1 = make_float4(k11 * K, p.opacity[i], rgb.x, rgb.y);
+        // alpha = min(0.99, opacity * exp(power)) = min(0.99, exp2(power' + log2(opacity)))
+        q1 = make_float4(k11 * K, log2f(p.opacity[i]), rgb.x, rgb.y);
         q2 = make_float4(rgb.z, pv[2], radius, 1.0f);
 
         // ---- quadtree membership: flags for nodes that split anyway, exact counts for leaf candidates ----
@@ -164,11 +193,14 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
                 const int fy = T.yf[o1 + iy];
                 for (int ix = xlo; ix <= xhi; ++ix) {
                     if (!axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) continue;
-                    uint32_t* c = cnt + (iy << l) + ix;
-                    if ((fy | T.xf[o1 + ix]) & QT_FLAG_BIG) {
-                        if (*(volatile uint32_t*)c == 0u) *c = 1u;  // non-empty flag
+                    const bool big = ((fy | T.xf[o1 + ix]) & QT_FLAG_BIG) != 0;
+                    n_touched += big ? 0u : 1u;
+                    if (use_hist) {
+                        atomicAdd(s_hist + off2(l) + (iy << l) + ix, 1u);
                     } else {
-                        atomicAdd(c, 1u);
+                        uint32_t* c = cnt + (iy << l) + ix;
+                        if (big) { if (*(volatile uint32_t*)c == 0u) *c = 1u; }  // non-empty flag
+                        else atomicAdd(c, 1u);
                     }
                 }
             }
@@ -176,11 +208,27 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
     }
     float4* rec = p.proj + 3 * i;
     rec[0] = q0; rec[1] = q1; rec[2] = q2;
+    p.depth_key[i] = in_front ? __float_as_uint(-pv[2]) : 0xFFFFFFFFu;
+    p.touched[i] = n_touched;
+  }
+    if (use_hist) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < p.nodes_2d; k += blockDim.x) {
+            const uint32_t v = s_hist[k];
+            if (v) atomicAdd(p.node_cnt + k, v);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// S4b.  Gaussians are visited in depth order (order[k] = k-th nearest); Gaussian order[k] writes one (leaf id, gid)
+// pair per leaf-candidate node it overlaps at offs[k].. — the leaf id is 0xFFFFFFFF when the node is not a leaf, so
+// the following stable radix sort on the leaf id leaves every leaf's list depth-ordered and the padding at the end.
 struct EmitParams {
     const float4* proj;
+    const uint32_t* order;
+    const uint32_t* incl;     // inclusive scan of touched[order[k]]
+    const uint32_t* touched;
     int64_t n;
     int32_t width, height;
     QtMeta meta;
@@ -188,23 +236,23 @@ struct EmitParams {
     int32_t n1;
     const uint8_t* node_state;
     const int32_t* leaf_of_node;
-    const int32_t* seg_begin;  // instance offset of every leaf
-    uint32_t* cursor;          // per-leaf fill counter (zero-filled by the caller)
-    unsigned long long* keys;  // (depth bits << 32) | Gaussian id
+    uint32_t* inst_leaf;
+    uint32_t* inst_gid;
 };
 
 __global__ void __launch_bounds__(256) emit_instances_kernel(const EmitParams p) {
     extern __shared__ int32_t smem_tab[];
     const QtTables T = load_tables(p.tab, p.n1, smem_tab);
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.n) return;
-    const float4 q2 = p.proj[3 * i + 2];
-    if (q2.w == 0.0f) return;
-    const float4 q0 = p.proj[3 * i];
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= p.n) return;
+    const uint32_t g = p.order[k];
+    const uint32_t nt = p.touched[g];
+    if (nt == 0u) return;
+    int64_t pos = (int64_t)p.incl[k] - nt;
+    const float4 q2 = p.proj[3 * (int64_t)g + 2];
+    const float4 q0 = p.proj[3 * (int64_t)g];
     float x0, x1, y0, y1;
     gaussian_rect(q0.x, q0.y, q2.z, p.width, p.height, x0, x1, y0, y1);
-    // nearest first: view-space z is negative in front of the camera, sort ascending by -z (gauss_render.py:340-344)
-    const unsigned long long key = ((unsigned long long)__float_as_uint(-q2.y) << 32) | (unsigned long long)(uint32_t)i;
     for (int l = 0; l < p.meta.num_levels; ++l) {
         const int o1 = (1 << l) - 1;
         int xlo, xhi, ylo, yhi;
@@ -215,13 +263,15 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(const EmitParams p)
         const int o2 = off2(l);
         for (int iy = ylo; iy <= yhi; ++iy) {
             if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy)) continue;
+            const int fy = T.yf[o1 + iy];
             for (int ix = xlo; ix <= xhi; ++ix) {
                 if (!axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) continue;
+                if ((fy | T.xf[o1 + ix]) & QT_FLAG_BIG) continue;  // not counted in touched[]
                 const int node = o2 + (iy << l) + ix;
-                if (p.node_state[node] != NODE_LEAF) continue;
-                const int leaf = p.leaf_of_node[node];
-                const uint32_t slot = atomicAdd(p.cursor + leaf, 1u);
-                p.keys[(int64_t)p.seg_begin[leaf] + slot] = key;
+                const uint32_t leaf = (p.node_state[node] == NODE_LEAF) ? (uint32_t)p.leaf_of_node[node] : 0xFFFFFFFFu;
+                p.inst_leaf[pos] = leaf;
+                p.inst_gid[pos] = g;
+                ++pos;
             }
         }
     }
@@ -239,10 +289,12 @@ QtTables make_tables(const int32_t* tables, int n1) {
 extern "C" int g2pc_preprocess(const float* xyz, const float* cov, const float* opacity, const float* colours,
                                const float* shs, int32_t sh_stride, int32_t sh_degree, int64_t n,
                                const g2pc_camera_t* cam_host, const int32_t* tables, int32_t num_levels,
-                               int32_t max_gaussians_per_tile, void* proj, uint32_t* node_cnt, void* stream) {
+                               int32_t max_gaussians_per_tile, void* proj, uint32_t* node_cnt, uint32_t* depth_key,
+                               uint32_t* touched, void* stream) {
     G2PC_CHECK_ARG(n >= 0, "n < 0");
     if (n == 0) return G2PC_OK;
-    G2PC_CHECK_ARG(xyz && cov && opacity && cam_host && tables && proj && node_cnt, "null pointer");
+    G2PC_CHECK_ARG(xyz && cov && opacity && cam_host && tables && proj && node_cnt && depth_key && touched,
+                   "null pointer");
     G2PC_CHECK_ARG((colours != nullptr) != (shs != nullptr), "provide exactly one of colours / shs");
     G2PC_CHECK_ARG(num_levels >= 1 && num_levels <= G2PC_MAX_LEVELS, "bad num_levels");
     G2PC_CHECK_ARG(!shs || (sh_degree >= 0 && sh_degree <= 3 && sh_stride >= (sh_degree + 1) * (sh_degree + 1)),
@@ -254,29 +306,33 @@ extern "C" int g2pc_preprocess(const float* xyz, const float* cov, const float* 
     p.meta.width = cam_host->width; p.meta.height = cam_host->height;
     p.n1 = (1 << num_levels) - 1;
     p.tab = make_tables(tables, p.n1);
-    p.proj = (float4*)proj; p.node_cnt = node_cnt;
-    const size_t smem = (size_t)6 * p.n1 * sizeof(int32_t);
+    p.proj = (float4*)proj; p.node_cnt = node_cnt; p.depth_key = depth_key; p.touched = touched;
+    const int nodes_2d = ((1 << (2 * num_levels)) - 1) / 3;
+    p.nodes_2d = nodes_2d <= 24 * 1024 ? nodes_2d : 0;  // histogram in shared memory when it fits (<= 96 KB)
+    const size_t smem = (size_t)6 * p.n1 * sizeof(int32_t) + (size_t)p.nodes_2d * sizeof(uint32_t);
     if (smem > 48 * 1024)
         G2PC_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    preprocess_kernel<<<(unsigned)((n + 255) / 256), 256, smem, (cudaStream_t)stream>>>(p);
+    preprocess_kernel<<<(unsigned)((n + PRE_PER_CTA - 1) / PRE_PER_CTA), 256, smem, (cudaStream_t)stream>>>(p);
     G2PC_CHECK_LAUNCH();
     return G2PC_OK;
 }
 
-extern "C" int g2pc_emit_instances(const void* proj, int64_t n, int32_t width, int32_t height, const int32_t* tables,
-                                   int32_t num_levels, const uint8_t* node_state, const int32_t* leaf_of_node,
-                                   const int32_t* seg_begin, uint32_t* cursor, uint64_t* keys, void* stream) {
+extern "C" int g2pc_emit_instances(const void* proj, const uint32_t* order, const uint32_t* incl,
+                                   const uint32_t* touched, int64_t n, int32_t width, int32_t height,
+                                   const int32_t* tables, int32_t num_levels, const uint8_t* node_state,
+                                   const int32_t* leaf_of_node, uint32_t* inst_leaf, uint32_t* inst_gid, void* stream) {
     G2PC_CHECK_ARG(n >= 0, "n < 0");
     if (n == 0) return G2PC_OK;
-    G2PC_CHECK_ARG(proj && tables && node_state && leaf_of_node && seg_begin && cursor && keys, "null pointer");
+    G2PC_CHECK_ARG(proj && order && incl && touched && tables && node_state && leaf_of_node && inst_leaf && inst_gid,
+                   "null pointer");
     G2PC_CHECK_ARG(num_levels >= 1 && num_levels <= G2PC_MAX_LEVELS, "bad num_levels");
     EmitParams p;
-    p.proj = (const float4*)proj; p.n = n; p.width = width; p.height = height;
+    p.proj = (const float4*)proj; p.order = order; p.incl = incl; p.touched = touched; p.n = n;
+    p.width = width; p.height = height;
     p.meta.num_levels = num_levels; p.meta.max_gaussians_per_tile = 0; p.meta.width = width; p.meta.height = height;
     p.n1 = (1 << num_levels) - 1;
     p.tab = make_tables(tables, p.n1);
-    p.node_state = node_state; p.leaf_of_node = leaf_of_node; p.seg_begin = seg_begin; p.cursor = cursor;
-    p.keys = (unsigned long long*)keys;
+    p.node_state = node_state; p.leaf_of_node = leaf_of_node; p.inst_leaf = inst_leaf; p.inst_gid = inst_gid;
     const size_t smem = (size_t)6 * p.n1 * sizeof(int32_t);
     if (smem > 48 * 1024)
         G2PC_CUDA(cudaFuncSetAttribute(emit_instances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

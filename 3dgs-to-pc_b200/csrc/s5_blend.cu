@@ -26,7 +26,8 @@ constexpr unsigned FULLM = 0xffffffffu;
 
 struct BlendParams {
     const g2pc_leaf_t* leaves;
-    const unsigned long long* keys;
+    const int32_t* leaf_order;
+    const uint32_t* inst_gid;
     const float4* proj;
     unsigned long long* cam_best;
     float* leaf_colour;
@@ -37,7 +38,7 @@ struct BlendParams {
 
 __device__ __forceinline__ float ex2f(float x) {
     float r;
-    asm("ex2.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // results below FLT_MIN flush to 0 (see header comment)
     return r;
 }
 
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(BT) blend_kernel(const BlendParams p) {
     __shared__ uint32_t s_gid[CH];
     __shared__ unsigned long long s_best[BT / 32][CH];
 
-    const g2pc_leaf_t lf = p.leaves[blockIdx.y];
+    const g2pc_leaf_t lf = p.leaves[p.leaf_order[blockIdx.y]];
     const int qpr = (lf.w + 3) >> 2;
     const int nquads = qpr * lf.h;
     const int quad0 = blockIdx.x * BT;
@@ -76,8 +77,7 @@ __global__ void __launch_bounds__(BT) blend_kernel(const BlendParams p) {
         const int nload = min(CH, cnt - base);
         if (__syncthreads_and(warp_done ? 1 : 0)) break;  // also orders the previous chunk's smem reads
         if (tid < nload) {
-            const unsigned long long key = p.keys[(int64_t)lf.inst_begin + base + tid];
-            const uint32_t gid = (uint32_t)key;
+            const uint32_t gid = p.inst_gid[(int64_t)lf.inst_begin + base + tid];
             const float4* rec = p.proj + 3 * (int64_t)gid;
             s_q0[tid] = __ldg(rec);
             s_q1[tid] = __ldg(rec + 1);
@@ -92,31 +92,27 @@ __global__ void __launch_bounds__(BT) blend_kernel(const BlendParams p) {
                 const float bl = s_b[j];
                 const float dy = py - q0.y;
                 const float Bq = dy * q0.w;
-                const float Cq = dy * dy * q1.x;
+                const float Cq = fmaf(dy * dy, q1.x, q1.y);  // + log2(opacity): alpha = min(0.99, exp2(e))
                 float c[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float dx = px[i] - q0.x;
                     const float e = fmaf(dx, fmaf(dx, q0.z, Bq), Cq);
-                    const float a = fminf(0.99f, ex2f(e) * q1.y);
+                    const float a = fminf(0.99f, ex2f(e));
                     c[i] = T[i] * a;
                     Cr[i] = fmaf(c[i], q1.z, Cr[i]);
                     Cg[i] = fmaf(c[i], q1.w, Cg[i]);
                     Cb[i] = fmaf(c[i], bl, Cb[i]);
                     T[i] -= c[i];
                 }
+                // warp max of the (non-negative) contributions, then the lowest pixel index among the lanes holding it
                 const float v = fmaxf(fmaxf(c[0], c[1]), fmaxf(c[2], c[3]));
                 const uint32_t vb = __float_as_uint(v);
                 const uint32_t wm = __reduce_max_sync(FULLM, vb);
-                if (wm != 0u) {
-                    const uint32_t ball = __ballot_sync(FULLM, vb == wm);
-                    if (lane == __ffs(ball) - 1) {
-                        const int i = (c[0] == v) ? 0 : (c[1] == v) ? 1 : (c[2] == v) ? 2 : 3;
-                        s_best[warp][j] = ((unsigned long long)wm << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(pix_row + i));
-                    }
-                } else if (lane == 0) {
-                    s_best[warp][j] = 0ull;
-                }
+                const int i = (c[0] == v) ? 0 : (c[1] == v) ? 1 : (c[2] == v) ? 2 : 3;
+                const uint32_t pk = (vb == wm) ? (0xFFFFFFFFu - (uint32_t)(pix_row + i)) : 0u;
+                const uint32_t wp = __reduce_max_sync(FULLM, pk);
+                if (lane == 0) s_best[warp][j] = wm ? (((unsigned long long)wm << 32) | (unsigned long long)wp) : 0ull;
             }
             const float tmax = fmaxf(fmaxf(T[0], T[1]), fmaxf(T[2], T[3]));
             warp_done = __all_sync(FULLM, tmax < 1.17549435e-38f);
@@ -193,15 +189,16 @@ __global__ void __launch_bounds__(256) compose_kernel(uint32_t* __restrict__ own
 
 }  // namespace
 
-extern "C" int g2pc_blend(const g2pc_leaf_t* leaves, int32_t num_leaves, int32_t max_leaf_pixels_quads,
-                          const uint64_t* keys, const void* proj, uint64_t* cam_best, float* leaf_colour,
-                          uint32_t* owner, int32_t width, int32_t height, float background, void* stream) {
+extern "C" int g2pc_blend(const g2pc_leaf_t* leaves, const int32_t* leaf_order, int32_t num_leaves,
+                          int32_t max_leaf_pixels_quads, const uint32_t* inst_gid, const void* proj,
+                          uint64_t* cam_best, float* leaf_colour, uint32_t* owner, int32_t width, int32_t height,
+                          float background, void* stream) {
     G2PC_CHECK_ARG(num_leaves >= 0, "negative size");
     if (num_leaves == 0) return G2PC_OK;
-    G2PC_CHECK_ARG(leaves && keys && proj && cam_best && leaf_colour && owner, "null pointer");
+    G2PC_CHECK_ARG(leaves && leaf_order && inst_gid && proj && cam_best && leaf_colour && owner, "null pointer");
     G2PC_CHECK_ARG(max_leaf_pixels_quads >= 1, "max_leaf_pixels_quads < 1");
     BlendParams p;
-    p.leaves = leaves; p.keys = (const unsigned long long*)keys; p.proj = (const float4*)proj;
+    p.leaves = leaves; p.leaf_order = leaf_order; p.inst_gid = inst_gid; p.proj = (const float4*)proj;
     p.cam_best = (unsigned long long*)cam_best; p.leaf_colour = leaf_colour; p.owner = owner;
     p.W = width; p.H = height; p.bg = background;
     const unsigned slabs = (unsigned)((max_leaf_pixels_quads + BT - 1) / BT);

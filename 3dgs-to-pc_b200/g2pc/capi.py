@@ -34,16 +34,18 @@ SIGNATURES = {
                           _c_void_p, _c_void_p, ctypes.c_int, _i64, _c_void_p], ctypes.c_int),
     "g2pc_dump_eps": ([_c_void_p, _i64, _i32, _i32, _u64, _u32, _c_void_p, _c_void_p], ctypes.c_int),
     "g2pc_preprocess": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i32, _i32, _i64, _c_void_p, _c_void_p,
-                         _i32, _i32, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
-    "g2pc_build_tree": ([_c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i32, _c_void_p,
-                         _c_void_p], ctypes.c_int),
-    "g2pc_emit_instances": ([_c_void_p, _i64, _i32, _i32, _c_void_p, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
-                             _c_void_p, _c_void_p], ctypes.c_int),
-    "g2pc_sort_workspace_bytes": ([_i64, _i32], ctypes.c_int64),
-    "g2pc_sort_leaves": ([_c_void_p, _c_void_p, _i64, _i32, _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p],
-                         ctypes.c_int),
-    "g2pc_blend": ([_c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i32, _i32, _f32,
-                    _c_void_p], ctypes.c_int),
+                         _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_depth_order_workspace_bytes": ([_i64], ctypes.c_int64),
+    "g2pc_depth_order": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p, _i64, _c_void_p], ctypes.c_int),
+    "g2pc_build_tree": ([_c_void_p, _i32, _i32, _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                         _c_void_p, _i32, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_emit_instances": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _i64, _i32, _i32, _c_void_p, _i32, _c_void_p,
+                             _c_void_p, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_sort_instances_workspace_bytes": ([_i64], ctypes.c_int64),
+    "g2pc_sort_instances": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _i64, _i32, _c_void_p, _i64, _c_void_p,
+                             _c_void_p], ctypes.c_int),
+    "g2pc_blend": ([_c_void_p, _c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i32, _i32,
+                    _f32, _c_void_p], ctypes.c_int),
     "g2pc_accumulate": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
     "g2pc_compose_image": ([_c_void_p, _c_void_p, _i32, _i32, _f32, _c_void_p, _c_void_p], ctypes.c_int),
 }
@@ -55,7 +57,8 @@ class Camera(ctypes.Structure):
                 ("tan_fovy", _f32), ("focal_x", _f32), ("focal_y", _f32), ("width", _i32), ("height", _i32)]
 
 
-HDR_NUM_LEAVES, HDR_TOTAL_INST, HDR_TOTAL_PIX, HDR_NEED_DEEPER, HDR_LEAF_OVERFLOW, HDR_WORDS = 0, 1, 2, 3, 4, 8
+HDR_NUM_LEAVES, HDR_TOTAL_INST, HDR_TOTAL_PIX, HDR_NEED_DEEPER, HDR_LEAF_OVERFLOW, HDR_TOTAL_UPPER = 0, 1, 2, 3, 4, 5
+HDR_WORDS = 8
 LEAF_WORDS = 8  # g2pc_leaf_t = 8 x int32
 
 _lib = None
@@ -87,7 +90,7 @@ def load(path=None):
 # ---- launch accounting (bench.py reads these) -------------------------------------------------------------------
 LAUNCHES = 0      # number of g2pc kernel entry points invoked since the last reset
 TIMING = None     # None, or {entry point name: [(start_event, end_event), ...]} to time launches with CUDA events
-_NOT_KERNELS = {"g2pc_version", "g2pc_last_error", "g2pc_sort_workspace_bytes"}
+_NOT_KERNELS = {"g2pc_version", "g2pc_last_error"}
 
 
 def call(name, *args):

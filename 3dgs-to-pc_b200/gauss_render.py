@@ -7,7 +7,7 @@ getters used by the pipeline (gauss_to_pc.py:481-513).
 
 `renderer_type="python"` reproduces GaussPythonRenderer (:210-465): quadtree tiles, every Gaussian of a tile blended
 into every pixel of the tile — but as sm_100a kernels behind the C ABI (csrc/s3_preprocess.cu, s4_tree.cu,
-s5_blend.cu), one camera = 7 launches + one 32-byte header read.  The tile parameters the reference derives from free
+s5_blend.cu), one camera = 9 entry-point calls + one 32-byte header read.  The tile parameters the reference derives from free
 GPU memory at call time (:440-444) are pinned (g2pc.config.MAX_TILE_SIZE / MAX_GAUSSIANS_PER_TILE).
 """
 import ctypes
@@ -74,8 +74,12 @@ class GaussPythonRenderer():
         # per-camera scratch, allocated once
         self._proj = torch.empty((n, 12), dtype=torch.float32, device=self.device)
         self._cam_best = torch.zeros((n,), dtype=torch.int64, device=self.device)
-        self._keys = None
-        self._keys_alt = None
+        self._depth_key = torch.empty((n,), dtype=torch.int32, device=self.device)
+        self._touched = torch.empty((n,), dtype=torch.int32, device=self.device)
+        self._order = torch.empty((n,), dtype=torch.int32, device=self.device)
+        self._incl = torch.empty((n,), dtype=torch.int32, device=self.device)
+        self._depth_ws = None
+        self._inst_leaf = self._inst_leaf_alt = self._inst_gid = self._inst_gid_alt = None
         self._leaf_colour = None
         self._sort_ws = None
         self._hdr_host = torch.zeros((capi.HDR_WORDS,), dtype=torch.int32).pin_memory()
@@ -113,7 +117,7 @@ class GaussPythonRenderer():
                      leaf_of_node=torch.full((qt.nodes_2d,), -1, dtype=torch.int32, device=dev),
                      leaves=torch.zeros((qt.nodes_2d, capi.LEAF_WORDS), dtype=torch.int32, device=dev),
                      seg_begin=torch.zeros((qt.nodes_2d + 1,), dtype=torch.int32, device=dev),
-                     cursor=torch.zeros((qt.nodes_2d,), dtype=torch.int32, device=dev),
+                     leaf_order=torch.zeros((qt.nodes_2d,), dtype=torch.int32, device=dev),
                      header=torch.zeros((capi.HDR_WORDS,), dtype=torch.int32, device=dev),
                      owner=torch.zeros((W * H,), dtype=torch.int32, device=dev),
                      image=torch.ones((H, W, 3), dtype=torch.float32, device=dev),
@@ -160,19 +164,24 @@ class GaussPythonRenderer():
         W, H = int(camera.image_width), int(camera.image_height)
         cam = self._camera_struct(camera)
         n = self._n
+        if self._depth_ws is None:
+            nbytes = lib.g2pc_depth_order_workspace_bytes(n)
+            self._depth_ws = torch.empty((max(int(nbytes), 1),), dtype=torch.uint8, device=self.device)
         while True:
             t = self._get_tables(W, H)
             qt = t["qt"]
             t["node_cnt"].zero_()
-            t["leaf_of_node"].fill_(-1)
             capi.call("g2pc_preprocess", capi.ptr(self.means3D), capi.ptr(self.cov3d), capi.ptr(self.opacity),
-                capi.ptr(self._colour_f32) if self.shs is None else None,
-                capi.ptr(self.shs), int(self.shs.shape[-1]) if self.shs is not None else 0, self.sh_degree, n,
-                ctypes.byref(cam), capi.ptr(t["tables"]), qt.num_levels, qt.max_gaussians_per_tile,
-                capi.ptr(self._proj), capi.ptr(t["node_cnt"]), st)
-            capi.call("g2pc_build_tree", capi.ptr(t["tables"]), qt.num_levels, qt.max_gaussians_per_tile, capi.ptr(t["node_cnt"]),
-                capi.ptr(t["node_state"]), capi.ptr(t["leaf_of_node"]), capi.ptr(t["leaves"]),
-                capi.ptr(t["seg_begin"]), qt.nodes_2d, capi.ptr(t["header"]), st)
+                      capi.ptr(self._colour_f32) if self.shs is None else None, capi.ptr(self.shs),
+                      int(self.shs.shape[-1]) if self.shs is not None else 0, self.sh_degree, n, ctypes.byref(cam),
+                      capi.ptr(t["tables"]), qt.num_levels, qt.max_gaussians_per_tile, capi.ptr(self._proj),
+                      capi.ptr(t["node_cnt"]), capi.ptr(self._depth_key), capi.ptr(self._touched), st)
+            capi.call("g2pc_depth_order", capi.ptr(self._depth_key), capi.ptr(self._touched), n,
+                      capi.ptr(self._order), capi.ptr(self._incl), capi.ptr(self._depth_ws), self._depth_ws.numel(), st)
+            capi.call("g2pc_build_tree", capi.ptr(t["tables"]), qt.num_levels, qt.max_gaussians_per_tile,
+                      capi.ptr(t["node_cnt"]), capi.ptr(self._incl), n, capi.ptr(t["node_state"]),
+                      capi.ptr(t["leaf_of_node"]), capi.ptr(t["leaves"]), capi.ptr(t["seg_begin"]),
+                      capi.ptr(t["leaf_order"]), qt.nodes_2d, capi.ptr(t["header"]), st)
             self._hdr_host.copy_(t["header"], non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()  # the one host read per camera (32 bytes)
             hdr = self._hdr_host.tolist()
@@ -185,35 +194,38 @@ class GaussPythonRenderer():
                 raise capi.G2pcError("leaf table overflow")
             break
         num_leaves, total_inst, total_pix = hdr[capi.HDR_NUM_LEAVES], hdr[capi.HDR_TOTAL_INST], hdr[capi.HDR_TOTAL_PIX]
+        total_upper = hdr[capi.HDR_TOTAL_UPPER]
         self.last_stats = dict(num_leaves=num_leaves, total_instances=total_inst, total_leaf_pixels=total_pix,
-                               levels=qt.num_levels)
+                               levels=qt.num_levels, instance_slots=total_upper)
         bg = 1.0 if self.white_bkgd else 0.0
         if num_leaves > 0 and total_inst > 0:
-            keys = self._grow("_keys", total_inst, torch.int64)
-            keys_alt = self._grow("_keys_alt", total_inst, torch.int64)
+            for name in ("_inst_leaf", "_inst_leaf_alt", "_inst_gid", "_inst_gid_alt"):
+                self._grow(name, total_upper, torch.int32)
             leaf_colour = self._grow("_leaf_colour", total_pix * 3, torch.float32)
-            t["cursor"][:num_leaves].zero_()
-            capi.call("g2pc_emit_instances", capi.ptr(self._proj), n, W, H, capi.ptr(t["tables"]), qt.num_levels, capi.ptr(t["node_state"]),
-                capi.ptr(t["leaf_of_node"]), capi.ptr(t["seg_begin"]), capi.ptr(t["cursor"]), capi.ptr(keys), st)
-            ws_bytes = lib.g2pc_sort_workspace_bytes(total_inst, num_leaves)
+            capi.call("g2pc_emit_instances", capi.ptr(self._proj), capi.ptr(self._order), capi.ptr(self._incl),
+                      capi.ptr(self._touched), n, W, H, capi.ptr(t["tables"]), qt.num_levels,
+                      capi.ptr(t["node_state"]), capi.ptr(t["leaf_of_node"]), capi.ptr(self._inst_leaf),
+                      capi.ptr(self._inst_gid), st)
+            ws_bytes = lib.g2pc_sort_instances_workspace_bytes(total_upper)
             if ws_bytes < 0:
                 raise capi.G2pcError("cub workspace query failed")
             ws = self._grow("_sort_ws", max(ws_bytes, 1), torch.uint8)
             in_alt = ctypes.c_int32(0)
-            capi.call("g2pc_sort_leaves", capi.ptr(keys), capi.ptr(keys_alt), total_inst, num_leaves,
-                                            capi.ptr(t["seg_begin"]), capi.ptr(ws), ws.numel(), ctypes.byref(in_alt),
-                                            st)
-            sorted_keys = keys_alt if in_alt.value else keys
-            self._last_sorted_keys = sorted_keys
-            capi.call("g2pc_blend", capi.ptr(t["leaves"]), num_leaves, t["max_quads"], capi.ptr(sorted_keys),
-                                      capi.ptr(self._proj), capi.ptr(self._cam_best), capi.ptr(leaf_colour),
-                                      capi.ptr(t["owner"]), W, H, bg, st)
+            # padding entries carry leaf id 0xFFFFFFFF: sorting on bit_length(num_leaves) bits puts them last
+            leaf_bits = max(1, int(num_leaves).bit_length())
+            capi.call("g2pc_sort_instances", capi.ptr(self._inst_leaf), capi.ptr(self._inst_leaf_alt),
+                      capi.ptr(self._inst_gid), capi.ptr(self._inst_gid_alt), total_upper, leaf_bits, capi.ptr(ws),
+                      ws.numel(), ctypes.byref(in_alt), st)
+            sorted_gid = self._inst_gid_alt if in_alt.value else self._inst_gid
+            self._last_sorted_gid = sorted_gid
+            capi.call("g2pc_blend", capi.ptr(t["leaves"]), capi.ptr(t["leaf_order"]), num_leaves, t["max_quads"],
+                      capi.ptr(sorted_gid), capi.ptr(self._proj), capi.ptr(self._cam_best), capi.ptr(leaf_colour),
+                      capi.ptr(t["owner"]), W, H, bg, st)
             capi.call("g2pc_accumulate", capi.ptr(self._cam_best), capi.ptr(leaf_colour), n,
-                                           capi.ptr(self.gaussian_max_contribution), capi.ptr(self.gaussian_colours),
-                                           st)
+                      capi.ptr(self.gaussian_max_contribution), capi.ptr(self.gaussian_colours), st)
             if self.compose_image:
                 capi.call("g2pc_compose_image", capi.ptr(t["owner"]), capi.ptr(leaf_colour), W, H, bg,
-                                                  capi.ptr(t["image"]), st)
+                          capi.ptr(t["image"]), st)
             else:
                 t["owner"].zero_()
         elif self.compose_image:
@@ -228,10 +240,11 @@ class GaussPythonRenderer():
         t = self._last_tables
         nl = self.last_stats["num_leaves"]
         leaves = t["leaves"][:nl].cpu().numpy()
-        keys = self._last_sorted_keys[: self.last_stats["total_instances"]].cpu().numpy() if nl else np.zeros(0, np.int64)
+        gids = (self._last_sorted_gid[: self.last_stats["total_instances"]].cpu().numpy().astype(np.int64)
+                if nl else np.zeros(0, np.int64))
         out = []
         for (r0, c0, w, h, beg, cnt, pix, node) in leaves:
-            out.append((int(r0), int(c0), int(w), int(h), (keys[beg:beg + cnt] & 0xFFFFFFFF).astype(np.int64)))
+            out.append((int(r0), int(c0), int(w), int(h), gids[beg:beg + cnt]))
         return self._proj.cpu().numpy(), out
 
 

@@ -127,8 +127,8 @@ int g2pc_dump_eps(const int64_t* gids, int64_t n_gids, int32_t k, int32_t attemp
 /* ---- S3-S6: colour stage, renderer_type=python semantics (gauss_render.py:101-465) ------------------------------ */
 /* Replaces GaussPythonRenderer.__call__/render (gauss_render.py:266-465) and — as the native op boundary — the role
  * of _C.rasterize_gaussians (rasterize_points.cu:36-145) in the per-camera loop of gauss_to_pc.py:437-454.
- * One camera = preprocess -> build_tree -> [host reads the 32-byte header] -> emit_instances -> sort_leaves -> blend
- * -> accumulate (-> compose_image). */
+ * One camera = preprocess -> depth_order -> build_tree -> [host reads the 32-byte header] -> emit_instances ->
+ * sort_instances -> blend -> accumulate (-> compose_image). */
 typedef struct {
     float view[16];  /* world_view_transform, row-vector convention p_view = [p,1] * V (camera_handler.py:46), row-major */
     float proj[16];  /* projection_matrix as stored by Camera (already transposed, camera_handler.py:48), row-major */
@@ -139,7 +139,7 @@ typedef struct {
 
 typedef struct {
     int32_t r0, c0, w, h;    /* first row / column and size of the leaf tile in pixels */
-    int32_t inst_begin;      /* offset of the leaf's list in the instance (key) array */
+    int32_t inst_begin;      /* offset of the leaf's list in the sorted instance arrays */
     int32_t inst_count;      /* Gaussians whose rect overlaps the leaf */
     int32_t pix_offset;      /* offset of the leaf's pixels in the concatenated leaf-colour buffer */
     int32_t node;            /* index of the quadtree node */
@@ -148,10 +148,11 @@ typedef struct {
 #define G2PC_MAX_LEVELS 12
 /* header words written by g2pc_build_tree (int32 each) */
 #define G2PC_HDR_NUM_LEAVES 0
-#define G2PC_HDR_TOTAL_INST 1
+#define G2PC_HDR_TOTAL_INST 1    /* sum of the leaves' instance counts */
 #define G2PC_HDR_TOTAL_PIX 2
 #define G2PC_HDR_NEED_DEEPER 3   /* a tile at the deepest tabulated level still has to split: re-run with more levels */
 #define G2PC_HDR_LEAF_OVERFLOW 4 /* more leaves than max_leaves */
+#define G2PC_HDR_TOTAL_UPPER 5   /* instance slots emit_instances fills (>= TOTAL_INST; the rest is padding) */
 #define G2PC_HDR_WORDS 8
 
 /* Quadtree tables (host-built, g2pc/quadtree.py): `tables` = 6 int32 arrays of n1 = 2^num_levels - 1 entries each,
@@ -162,39 +163,52 @@ typedef struct {
  * :101-148), radius / rect (:171-193), conic = inverse(cov2d) (:349) pre-scaled by -0.5*log2(e), colour (given, or SH
  * deg <= 3 evaluated towards the camera: eval_sh :43-99 + 0.5, clamped at 0), and tile-membership counting for every
  * tabulated level.  xyz (n,3) · cov (n,3,3) · opacity (n) · colours (n,3) f32 or NULL · shs (n,3,sh_stride) f32 channel-
- * major or NULL.  proj: n x 48 bytes (3 float4: {mx,my,c00',c01'} {c11',opacity,r,g} {b,depth,radius,valid}).
- * node_cnt: one uint32 per 2-D node, zero-filled by the caller. */
+ * major or NULL.  proj: n x 48 bytes (3 float4: {mx,my,c00',c01'} {c11',log2(opacity),r,g} {b,depth,radius,valid}).
+ * node_cnt: one uint32 per 2-D node, zero-filled by the caller.  depth_key (n) uint32: bits(-z_view), 0xFFFFFFFF
+ * if behind the camera.  touched (n) uint32: leaf-candidate nodes overlapped (upper bound of the instances). */
 int g2pc_preprocess(const float* xyz, const float* cov, const float* opacity, const float* colours,
                     const float* shs, int32_t sh_stride, int32_t sh_degree, int64_t n,
                     const g2pc_camera_t* cam_host, const int32_t* tables, int32_t num_levels,
-                    int32_t max_gaussians_per_tile, void* proj, uint32_t* node_cnt, void* stream);
+                    int32_t max_gaussians_per_tile, void* proj, uint32_t* node_cnt, uint32_t* depth_key,
+                    uint32_t* touched, void* stream);
 
-/* S4a.  Resolve the quadtree (one CTA): node states, leaves in the reference's BFS order with instance / pixel
- * offsets, seg_begin[leaf] (max_leaves + 1 entries), header.  node_state: uint8 per node · leaf_of_node: int32 per node. */
+/* S4a.  order[k] = index of the k-th nearest Gaussian (stable radix sort of depth_key: ties keep index order, the
+ * reference's torch.sort is unstable there, gauss_render.py:340-344); incl[k] = inclusive prefix sum of
+ * touched[order[k]].  cub::DeviceRadixSort + cub::DeviceScan. */
+int64_t g2pc_depth_order_workspace_bytes(int64_t n);
+int g2pc_depth_order(const uint32_t* depth_key, const uint32_t* touched, int64_t n, uint32_t* order, uint32_t* incl,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* S4b.  Resolve the quadtree (one CTA): node states, leaves in the reference's BFS order with instance / pixel
+ * offsets, seg_begin[leaf] (max_leaves + 1 entries), leaf_order (heaviest leaf first, the blend's launch order),
+ * header.  node_state: uint8 per node · leaf_of_node: int32 per node.  incl/n: from g2pc_depth_order (may be NULL/0). */
 int g2pc_build_tree(const int32_t* tables, int32_t num_levels, int32_t max_gaussians_per_tile,
-                    const uint32_t* node_cnt, uint8_t* node_state, int32_t* leaf_of_node, g2pc_leaf_t* leaves,
-                    int32_t* seg_begin, int32_t max_leaves, int32_t* header, void* stream);
+                    const uint32_t* node_cnt, const uint32_t* incl, int64_t n, uint8_t* node_state,
+                    int32_t* leaf_of_node, g2pc_leaf_t* leaves, int32_t* seg_begin, int32_t* leaf_order,
+                    int32_t max_leaves, int32_t* header, void* stream);
 
-/* S4b.  Per Gaussian and member leaf: keys[seg_begin[leaf] + slot] = (bits(-z_view) << 32) | Gaussian id.
- * cursor: uint32 per leaf, zero-filled by the caller. */
-int g2pc_emit_instances(const void* proj, int64_t n, int32_t width, int32_t height, const int32_t* tables,
-                        int32_t num_levels, const uint8_t* node_state, const int32_t* leaf_of_node,
-                        const int32_t* seg_begin, uint32_t* cursor, uint64_t* keys, void* stream);
+/* S4c.  In depth order: Gaussian order[k] writes (leaf id | 0xFFFFFFFF, Gaussian id) for every leaf-candidate node it
+ * overlaps at slots [incl[k] - touched, incl[k]). */
+int g2pc_emit_instances(const void* proj, const uint32_t* order, const uint32_t* incl, const uint32_t* touched,
+                        int64_t n, int32_t width, int32_t height, const int32_t* tables, int32_t num_levels,
+                        const uint8_t* node_state, const int32_t* leaf_of_node, uint32_t* inst_leaf,
+                        uint32_t* inst_gid, void* stream);
 
-/* S4c.  Sort every leaf's keys ascending (nearest first, ties by Gaussian id) — cub::DeviceSegmentedSort.
- * *sorted_in_alt_host = 1 if the result ended in keys_alt.  (The only entry point that writes a host word.) */
-int64_t g2pc_sort_workspace_bytes(int64_t num_items, int32_t num_segments);
-int g2pc_sort_leaves(uint64_t* keys, uint64_t* keys_alt, int64_t num_items, int32_t num_segments,
-                     const int32_t* seg_begin, void* workspace, int64_t workspace_bytes,
-                     int32_t* sorted_in_alt_host, void* stream);
+/* S4d.  Stable radix sort of the instance pairs on the low leaf_bits bits of the leaf id (cub::DeviceRadixSort): the
+ * leaves' lists become contiguous ([seg_begin[l], seg_begin[l+1])) and stay depth-ordered.
+ * *sorted_in_alt_host = 1 if the result ended in the *_alt buffers.  (The only entry point that writes a host word.) */
+int64_t g2pc_sort_instances_workspace_bytes(int64_t num_items);
+int g2pc_sort_instances(uint32_t* inst_leaf, uint32_t* inst_leaf_alt, uint32_t* inst_gid, uint32_t* inst_gid_alt,
+                        int64_t num_items, int32_t leaf_bits, void* workspace, int64_t workspace_bytes,
+                        int32_t* sorted_in_alt_host, void* stream);
 
 /* S5.  Front-to-back blend of every leaf (gauss_render.py:337-369) + per-Gaussian maximum contribution / arg-max pixel
  * (:371-385) published as cam_best[g] = max((bits(contribution) << 32) | ~leaf_pixel_index).
  * max_leaf_pixels_quads: upper bound of ceil(w/4)*h over the leaves.  leaf_colour: (total_pix,3) f32.
  * owner: uint32 per image pixel (zero-filled): 1 + index of the last leaf pixel covering it. */
-int g2pc_blend(const g2pc_leaf_t* leaves, int32_t num_leaves, int32_t max_leaf_pixels_quads, const uint64_t* keys,
-               const void* proj, uint64_t* cam_best, float* leaf_colour, uint32_t* owner, int32_t width,
-               int32_t height, float background, void* stream);
+int g2pc_blend(const g2pc_leaf_t* leaves, const int32_t* leaf_order, int32_t num_leaves, int32_t max_leaf_pixels_quads,
+               const uint32_t* inst_gid, const void* proj, uint64_t* cam_best, float* leaf_colour, uint32_t* owner,
+               int32_t width, int32_t height, float background, void* stream);
 
 /* S6.  Fold one camera into the per-Gaussian accumulators (gauss_render.py:387-395; the role of
  * GaussianRasterizer.update_max_contributions, gaussian_pointcloud_rasterization/__init__.py:142-152):

@@ -49,8 +49,10 @@ def test_cov_normals_magnitudes(lib):
     assert float(((G.covariances.cpu() - cov).abs() / scale).max()) < 2e-6  # +5e-7*I on (nearly) identical inputs
     m = G.get_gaussian_magnitudes().cpu()
     assert m.dtype == torch.float64
-    rel = ((m - mags).abs() / mags).max()
-    assert float(rel) < 2e-5, f"magnitudes rel err {float(rel)}"
+    # the oracle's eigenvalues come from LAPACK's general f32 solver (abs error ~1e-7 * lambda_max, i.e. a relative error
+    # up to ~1e-4 on the smallest eigenvalue of a flat Gaussian); the kernel's closed form is evaluated in f64
+    rel = (m - mags).abs() / mags
+    assert float(rel.max()) < 5e-4 and float(rel.median()) < 2e-6, f"magnitudes rel err {float(rel.max())}"
 
 
 @pytest.mark.parametrize("n,num_points,exact,attempts,cull_mode", [
