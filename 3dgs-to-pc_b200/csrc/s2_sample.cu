@@ -26,6 +26,7 @@ struct CountParams {
     int colour_dtype;
     const float* normals;
     const int32_t* perm;
+    const uint32_t* gids;
     int64_t gid_offset;
     int64_t n;
     const g2pc_tile_t* tiles;
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(BLOCK) sample_count_kernel(const CountParams p
     if (active) {
         const int64_t j = (int64_t)t.j0 + g;
         const int64_t idx = p.perm[j];
-        gid = (uint32_t)(idx + p.gid_offset);
+        gid = p.gids ? p.gids[idx] : (uint32_t)(idx + p.gid_offset);
         mu = make_float3(p.xyz[3 * idx], p.xyz[3 * idx + 1], p.xyz[3 * idx + 2]);
         float a[9];
 #pragma unroll
@@ -378,7 +379,8 @@ __global__ void dump_eps_kernel(const int64_t* __restrict__ gids, int64_t n_gids
 }  // namespace
 
 extern "C" int g2pc_sample_count(const float* xyz, const float* cov, const void* colours, int colour_dtype,
-                                 const float* normals, const int32_t* perm, int64_t gid_offset, int64_t n,
+                                 const float* normals, const int32_t* perm, const uint32_t* gids, int64_t gid_offset,
+                                 int64_t n,
                                  const g2pc_tile_t* tiles, int32_t num_tiles, int32_t num_attempts,
                                  int32_t attempts_stored, float mahalanobis_std, int32_t cull_mode, uint64_t seed,
                                  uint32_t call_id, void* records, uint32_t* xl, uint32_t* tile_totals,
@@ -393,7 +395,7 @@ extern "C" int g2pc_sample_count(const float* xyz, const float* cov, const void*
     G2PC_CHECK_ARG(((uintptr_t)records & 15) == 0, "records must be 16-byte aligned");
     CountParams p;
     p.xyz = xyz; p.cov = cov; p.colours = colours; p.colour_dtype = colour_dtype; p.normals = normals;
-    p.perm = perm; p.gid_offset = gid_offset; p.n = n; p.tiles = tiles; p.num_attempts = num_attempts;
+    p.perm = perm; p.gids = gids; p.gid_offset = gid_offset; p.n = n; p.tiles = tiles; p.num_attempts = num_attempts;
     p.attempts_stored = attempts_stored; p.std = mahalanobis_std;
     p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32); p.call_id = call_id;
     p.records = (float4*)records; p.xl = xl; p.tile_totals = tile_totals; p.status = status;

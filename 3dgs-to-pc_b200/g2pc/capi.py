@@ -27,7 +27,7 @@ SIGNATURES = {
     "g2pc_cov_build": ([_c_void_p, _c_void_p, ctypes.c_int, _f32, _i64, _c_void_p, _c_void_p], ctypes.c_int),
     "g2pc_normals": ([_c_void_p, _c_void_p, ctypes.c_int, _i64, _c_void_p, _c_void_p], ctypes.c_int),
     "g2pc_eigvals_sym3": ([_c_void_p, _i64, _c_void_p, _c_void_p], ctypes.c_int),
-    "g2pc_sample_count": ([_c_void_p, _c_void_p, _c_void_p, ctypes.c_int, _c_void_p, _c_void_p, _i64, _i64,
+    "g2pc_sample_count": ([_c_void_p, _c_void_p, _c_void_p, ctypes.c_int, _c_void_p, _c_void_p, _c_void_p, _i64, _i64,
                            _c_void_p, _i32, _i32, _i32, _f32, _i32, _u64, _u32, _c_void_p, _c_void_p, _c_void_p,
                            _c_void_p, _c_void_p], ctypes.c_int),
     "g2pc_sample_emit": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _i32, _u64, _u32, _c_void_p,

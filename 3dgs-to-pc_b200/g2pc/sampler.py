@@ -133,7 +133,7 @@ class SamplePlan:
 
 
 def run_plan(plan, xyz, cov, colours, normals, perm, num_attempts, std, seed, call_id, gid_offset=0,
-             out_dtype=None, cull_mode=None, want_normals=True):
+             out_dtype=None, cull_mode=None, want_normals=True, gids=None):
     """Launch the two S2 kernels for `plan`.  All tensors on one CUDA device.  Returns
     (points, colours, normals|None, total_tensor, status_tensor) with outputs sized plan.capacity (valid rows:
     [0, total))."""
@@ -156,6 +156,9 @@ def run_plan(plan, xyz, cov, colours, normals, perm, num_attempts, std, seed, ca
         normals = normals.contiguous().to(torch.float32)
     perm = perm.to(torch.int32).contiguous()
     assert perm.shape[0] == n
+    if gids is not None:
+        gids = gids.to(torch.int32).contiguous()  # uint32 bit pattern
+        assert gids.shape[0] == xyz.shape[0]
 
     tiles_d = torch.from_numpy(plan.tiles).to(dev, non_blocking=True)
     units_d = torch.from_numpy(plan.units).to(dev, non_blocking=True)
@@ -168,7 +171,7 @@ def run_plan(plan, xyz, cov, colours, normals, perm, num_attempts, std, seed, ca
     status = torch.zeros((capi.ST_WORDS,), dtype=torch.int32, device=dev)
 
     capi.call("g2pc_sample_count", capi.ptr(xyz), capi.ptr(cov), capi.ptr(colours), capi.dtype_code(colours), capi.ptr(normals),
-        capi.ptr(perm), int(gid_offset), n, capi.ptr(tiles_d), nt, int(num_attempts), A, float(std),
+        capi.ptr(perm), capi.ptr(gids), int(gid_offset), n, capi.ptr(tiles_d), nt, int(num_attempts), A, float(std),
         int(cull_mode), int(seed) & 0xFFFFFFFFFFFFFFFF, int(call_id) & 0xFFFFFFFF, capi.ptr(records), capi.ptr(xl),
         capi.ptr(tile_totals), capi.ptr(status), st)
 

@@ -92,6 +92,9 @@ class Gaussians():
         self.colours = colours
         self.shs = shs
         self.normals = None
+        # original row of every Gaussian: follows the culls, keys the sampler's RNG (so that the drawn points do not
+        # depend on how the array is culled or sharded)
+        self.ids = torch.arange(xyz.shape[0], dtype=torch.int32, device=xyz.device)
 
         self.scaling_modifier = 1.0
 
@@ -179,6 +182,8 @@ class Gaussians():
 
         if self.normals is not None:
             self.normals = self.normals[keep]
+
+        self.ids = self.ids[keep]
 
         self.set_default_filter()
 

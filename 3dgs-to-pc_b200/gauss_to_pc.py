@@ -165,7 +165,7 @@ def generate_pointcloud(gaussians, num_points, contributions=None, mahalanobis_d
     res = sample_points_per_gaussian(gaussians.xyz, gaussians.covariances, gaussians.colours,
                                      gaussians.normals if calculate_normals else None, points_per_gaussian,
                                      mahalanobis_distance_std, exact_num_points, num_sample_attempts, seed, call_id,
-                                     gid_offset=gid_offset, quiet=quiet)
+                                     gid_offset=gid_offset, quiet=quiet, gids=getattr(gaussians, "ids", None))
     pts, cols, nrm, total, status, dbg = res
     t = int(total.item())  # the one sync of the stage (the reference syncs per bin and per attempt)
     _check_status(status)
@@ -177,14 +177,20 @@ def generate_pointcloud(gaussians, num_points, contributions=None, mahalanobis_d
 
 def sample_points_per_gaussian(xyz, covariances, colours, normals, points_per_gaussian, mahalanobis_distance_std,
                                exact_num_points, num_sample_attempts, seed, call_id, gid_offset=0, quiet=True,
-                               hist=None):
+                               hist=None, gids=None, global_bins=None):
     """Bin planning on the host (from the histogram, as the reference does) + the two S2 kernels.
-    Everything is enqueued asynchronously; the caller syncs once on the returned total."""
+    Everything is enqueued asynchronously; the caller syncs once on the returned total.
+    gids: global Gaussian id per row (keys the RNG; survives culls / sharding).  global_bins: bins planned on the
+    histogram of ALL ranks (g2pc.dist); the local member counts are taken from this rank's histogram."""
     dev = xyz.device
     ppg = points_per_gaussian.to(torch.int64)
     if hist is None:
         hist = torch.bincount(ppg).cpu().numpy()  # host needs the histogram to lay out bins (reference: :110-115)
-    bins = sampler.plan_bins(hist, exact_num_points)
+    if global_bins is not None:
+        from g2pc import dist as gdist
+        bins = [b for b in gdist.local_bin_counts(global_bins, hist) if b[3] > 0]
+    else:
+        bins = sampler.plan_bins(hist, exact_num_points)
     if not quiet:
         print("Starting Point Cloud Generation")
 
@@ -204,7 +210,7 @@ def sample_points_per_gaussian(xyz, covariances, colours, normals, points_per_ga
     plan = sampler.SamplePlan([(n - 1, count) for (_, _, n, count) in bins], A, include_centres=True)
     pts, cols, nrm, total, status, bufs = sampler.run_plan(
         plan, xyz.to(torch.float32), covariances.to(torch.float32), colours, normals, perm, num_sample_attempts,
-        mahalanobis_distance_std, seed, call_id, gid_offset=gid_offset, want_normals=normals is not None)
+        mahalanobis_distance_std, seed, call_id, gid_offset=gid_offset, want_normals=normals is not None, gids=gids)
     dbg = {"bins": bins, "perm": perm, "plan": plan, "buffers": bufs}
     return pts, cols, nrm, total, status, dbg
 

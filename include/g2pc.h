@@ -96,12 +96,12 @@ typedef struct {
  * m = min(k - added, count), and write the tile-local exclusive prefix of m
  * (xl[attempt*n + j]) and the tile total (tile_totals[tile*attempts_stored + attempt]).
  *   xyz (N,3) f32 · cov (N,3,3) f32 · colours (N,3) colour_dtype · normals (N,3) f32 or NULL
- *   perm (n,) int32: bin-order index -> row of the input arrays;  gid_offset: added to perm[j] to form the
- *   global Gaussian id that keys the RNG (rank offset when the Gaussian array is sharded)
+ *   perm (n,) int32: bin-order index -> row of the input arrays;  the RNG is keyed by the global Gaussian id
+ *   gids[row] (uint32 per input row; survives culls and sharding) or, if gids is NULL, row + gid_offset
  *   records: n*64 bytes, 16-byte aligned · xl: attempts_stored*n uint32 · tile_totals: num_tiles*attempts_stored
  *   uint32, MUST be zero-filled by the caller · status: G2PC_ST_WORDS int32, zero-filled by the caller. */
 int g2pc_sample_count(const float* xyz, const float* cov, const void* colours, int colour_dtype,
-                      const float* normals, const int32_t* perm, int64_t gid_offset, int64_t n,
+                      const float* normals, const int32_t* perm, const uint32_t* gids, int64_t gid_offset, int64_t n,
                       const g2pc_tile_t* tiles, int32_t num_tiles, int32_t num_attempts,
                       int32_t attempts_stored, float mahalanobis_std, int32_t cull_mode, uint64_t seed,
                       uint32_t call_id, void* records, uint32_t* xl, uint32_t* tile_totals,
