@@ -54,13 +54,39 @@ def make_sampling(name, n, scene_seed, num_points, exact, attempts, rng_seed):
     print(name, "points", tuple(pts.shape), "mvn calls", calls.shape[0])
 
 
+COLOUR_CASES = {
+    # name: (n_gaussians, scene_seed, n_cameras, colour_resolution)
+    "colour_a": (2500, 1310, 2, 200),
+    "colour_b": (1200, 1311, 3, 180),
+}
+
+
+def make_colour(name, n, scene_seed, ncams, res):
+    """GaussPythonRenderer of the reference (gauss_render.py:210-465), tile parameters pinned to (60, 60000)."""
+    ref = ref_shim.load()
+    sc = synth.make_scene(n, seed=scene_seed)
+    cams, intr = synth.make_cameras(ncams)
+    with ref_shim.cpu_redirect(pinned_tiles=(60, 60000)):
+        G = ref.gauss_handler.Gaussians(sc["xyz"].clone(), sc["scales"].clone(), sc["rots"].clone(),
+                                        sc["colours"].clone(), sc["opacities"].clone())
+        R = ref.gauss_render.get_renderer("python", G.xyz, torch.unsqueeze(torch.clone(G.opacities), 1), G.colours,
+                                          G.covariances, visible_gaussian_threshold=0.05)
+        imgs = []
+        for c2w, k in zip(cams, intr):
+            cam = ref.camera_handler.get_camera("python", c2w.clone(), k, colour_resolution=res)
+            img, _, _, _ = R(cam)
+            imgs.append(img.numpy().astype(np.float32))
+        np.savez_compressed(os.path.join(HERE, name + ".npz"),
+                            meta=np.array([n, scene_seed, ncams, res], dtype=np.int64),
+                            max_contribution=R.gaussian_max_contribution.numpy(),
+                            colours=R.gaussian_colours.numpy(), images=np.stack(imgs),
+                            visible=R.get_visible_gaussians().numpy())
+    print(name, "images", np.stack(imgs).shape, "seen", int((R.gaussian_max_contribution > 0).sum()))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     for name, args in SAMPLING_CASES.items():
         make_sampling(name, *args)
-    if "--colour" in sys.argv or True:
-        try:
-            from make_golden_colour import make_all
-            make_all()
-        except ImportError:
-            pass
+    for name, args in COLOUR_CASES.items():
+        make_colour(name, *args)

@@ -49,6 +49,26 @@ def test_sampling_oracle_matches_reference_golden(name):
     assert np.array_equal(np.array(calls, dtype=np.int64), g["mvn_calls"])
 
 
+@pytest.mark.parametrize("name", ["colour_a", "colour_b"])
+def test_colour_oracle_matches_reference_golden(name):
+    """oracle/render.py against the unmodified reference renderer's outputs (tile parameters pinned to (60, 60000))."""
+    from g2pc import synth
+    from oracle import gaussians as og, render as orr
+    g = _load(name)
+    n, scene_seed, ncams, res = [int(v) for v in g["meta"]]
+    sc = synth.make_scene(n, seed=scene_seed)
+    cams, intr = synth.make_cameras(ncams)
+    cov = og.build_covariance(sc["scales"], sc["rots"])
+    for dense in (False, True):
+        O = orr.PythonRendererOracle(sc["xyz"], sc["opacities"], sc["colours"], cov, dense=dense)
+        for i, (c2w, k) in enumerate(zip(cams, intr)):
+            img = O(orr.Camera(c2w, k, colour_resolution=res))
+            assert np.abs(img - g["images"][i]).max() < 2e-6
+        assert np.abs(O.gaussian_max_contribution - g["max_contribution"]).max() < 2e-6
+        assert np.abs(O.gaussian_colours - g["colours"]).max() < 2e-6
+        assert np.array_equal(O.gaussian_max_contribution > 0.05, g["visible"]), "visibility mask must be exact"
+
+
 def test_philox_known_answers():
     """Random123 known-answer vectors for Philox4x32-10."""
     from oracle.philox import philox4x32_10
