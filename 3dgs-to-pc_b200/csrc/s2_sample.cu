@@ -10,8 +10,9 @@
 //
 // Pass 1 (sample_count_kernel): one CTA per tile.  Gathers the tile's Gaussians, factors Sigma, packs a 64-byte
 //   record per Gaussian in bin order, simulates the attempt loop and writes per-attempt tile-local prefixes.
-// Pass 2 (sample_emit_kernel): one CTA per 1024 OUTPUT points (4 consecutive points per thread); positions are
-//   staged in shared memory and leave as 16-byte coalesced stores.  RNG is regenerated, never stored.
+// Pass 2 (sample_emit_kernel): one CTA per 512 OUTPUT points; runs are expanded into a per-point table in shared
+//   memory, points are generated divergence-free (4 per thread, strided), staged in shared memory and leave as
+//   16-byte coalesced stores.  RNG is regenerated, never stored.
 #include "common.cuh"
 
 namespace {
@@ -232,6 +233,7 @@ struct EmitParams {
     int64_t n;
     const g2pc_unit_t* units;
     const int64_t* unit_base;
+    const int32_t* chunk_unit;  // chunk_unit[c] = unit holding output point c*1024 (host-side searchsorted); may be null
     int32_t num_units;
     uint32_t k0, k1, call_id;
     float* out_xyz;
@@ -241,8 +243,8 @@ struct EmitParams {
     int64_t capacity;
 };
 
-constexpr int PTS_PER_THREAD = 4;
-constexpr int TILE_PTS = BLOCK * PTS_PER_THREAD;  // 1024
+constexpr int PTS_PER_THREAD = 2;
+constexpr int TILE_PTS = BLOCK * PTS_PER_THREAD;  // 512 output points per CTA
 
 // last u in [lo, hi] with unit_base[u] <= p   (unit_base non-decreasing; zero-length units are skipped over)
 __device__ __forceinline__ int find_unit(const int64_t* __restrict__ base, int lo, int hi, int64_t p) {
@@ -271,18 +273,16 @@ __device__ __forceinline__ void flush_tile(const float* s, OUT_T* out, int64_t p
         if (full) {
             const float4* s4 = reinterpret_cast<const float4*>(s);
             float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll
-            for (int i = 0; i < TILE_PTS * 3 / 4 / BLOCK; ++i) o4[threadIdx.x + i * BLOCK] = s4[threadIdx.x + i * BLOCK];
+            for (int k = threadIdx.x; k < TILE_PTS * 3 / 4; k += BLOCK) o4[k] = s4[k];
             return;
         }
     } else {
         if (full) {
             const float2* s2 = reinterpret_cast<const float2*>(s);
             double2* o2 = reinterpret_cast<double2*>(o);
-#pragma unroll
-            for (int i = 0; i < TILE_PTS * 3 / 2 / BLOCK; ++i) {
-                const float2 v = s2[threadIdx.x + i * BLOCK];
-                o2[threadIdx.x + i * BLOCK] = make_double2((double)v.x, (double)v.y);
+            for (int k = threadIdx.x; k < TILE_PTS * 3 / 2; k += BLOCK) {
+                const float2 v = s2[k];
+                o2[k] = make_double2((double)v.x, (double)v.y);
             }
             return;
         }
@@ -290,74 +290,150 @@ __device__ __forceinline__ void flush_tile(const float* s, OUT_T* out, int64_t p
     for (int i = threadIdx.x; i < npts * 3; i += BLOCK) o[i] = (OUT_T)s[i];
 }
 
+constexpr int NU_STAGE = 8;  // units whose descriptors / prefix rows are staged in shared memory per chunk
+
+// last i in [0, count) with xs[i] <= q, xs in shared memory
+__device__ __forceinline__ int find_run_smem(const uint32_t* xs, int count, uint32_t q) {
+    int lo = 0, hi = count - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (xs[mid] <= q) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+constexpr uint32_t CENTRE_TAG = 0xFF000000u;
+
+// Pass 2, three phases per 512-point chunk:
+//   A  stage the descriptors / bases / prefix rows of the (few) units the chunk overlaps in shared memory;
+//   B  expand runs into a per-point (record index, attempt|sample) table: one thread per run for small k (no search
+//      at all), one thread per point with a shared-memory binary search for large k;
+//   C  uniform, divergence-free generation: thread t handles points t and t+256 (independent record
+//      loads in flight, conflict-free staging), then 16-byte coalesced stores.
 template <typename OUT_T, bool HAS_NRM>
-__global__ void __launch_bounds__(BLOCK) sample_emit_kernel(const EmitParams p) {
+__global__ void __launch_bounds__(BLOCK, 6) sample_emit_kernel(const EmitParams p) {
     __shared__ __align__(16) float s_xyz[TILE_PTS * 3];
     __shared__ __align__(16) float s_rgb[TILE_PTS * 3];
     __shared__ __align__(16) float s_nrm[HAS_NRM ? TILE_PTS * 3 : 4];
+    // the per-point table lives in the xyz staging area: it is dead before the positions are written (barrier below)
+    uint32_t* s_j = reinterpret_cast<uint32_t*>(s_xyz);
+    uint32_t* s_s = s_j + TILE_PTS;
     __shared__ int s_urange[2];
+    __shared__ int64_t s_ubase[NU_STAGE + 1];
+    __shared__ g2pc_unit_t s_units[NU_STAGE];
+    __shared__ uint32_t s_xl[NU_STAGE][BLOCK];
 
     const int64_t total = __ldg(p.unit_base + p.num_units);
     const int64_t p0 = (int64_t)blockIdx.x * TILE_PTS;
     if (p0 >= total) return;
     const int64_t pend = (p0 + TILE_PTS < total) ? p0 + TILE_PTS : total;
     const int npts = (int)(pend - p0);
+    const int tid = threadIdx.x;
 
-    if (threadIdx.x < 2) {
-        const int64_t q = threadIdx.x == 0 ? p0 : pend - 1;
-        s_urange[threadIdx.x] = find_unit(p.unit_base, 0, p.num_units - 1, q);
+    int u_lo, u_hi;
+    if (p.chunk_unit) {
+        // chunk c+1 starts at pend (or beyond the total): its unit bounds this chunk's range from above
+        u_lo = p.chunk_unit[blockIdx.x];
+        u_hi = min(p.chunk_unit[blockIdx.x + 1], p.num_units - 1);
+    } else {
+        if (tid < 2) {
+            const int64_t q = tid == 0 ? p0 : pend - 1;
+            s_urange[tid] = find_unit(p.unit_base, 0, p.num_units - 1, q);
+        }
+        __syncthreads();
+        u_lo = s_urange[0]; u_hi = s_urange[1];
+    }
+    const int nu = u_hi - u_lo + 1;
+    if (nu <= NU_STAGE) {  // uniform per CTA
+        // ---- phase A ----
+        if (tid <= nu) s_ubase[tid] = __ldg(p.unit_base + u_lo + tid);
+        if (tid < nu) s_units[tid] = p.units[u_lo + tid];
+        __syncthreads();
+        for (int ui = 0; ui < nu; ++ui) {
+            const g2pc_unit_t un = s_units[ui];
+            if (un.attempt >= 0 && tid < un.count)
+                s_xl[ui][tid] = __ldg(p.xl + (int64_t)un.attempt * p.n + un.j0 + tid);
+        }
+        __syncthreads();
+        // ---- phase B ----
+        for (int ui = 0; ui < nu; ++ui) {
+            const g2pc_unit_t un = s_units[ui];
+            const int64_t lb = s_ubase[ui], le = s_ubase[ui + 1];
+            const int64_t cb = lb > p0 ? lb : p0, ce = le < pend ? le : pend;
+            if (ce <= cb) continue;
+            if (un.attempt < 0) {
+                for (int64_t pt = cb + tid; pt < ce; pt += BLOCK) {
+                    s_j[pt - p0] = (uint32_t)(un.j0 + (pt - lb));
+                    s_s[pt - p0] = CENTRE_TAG;
+                }
+            } else if (un.k <= 16) {
+                if (tid < un.count) {
+                    const int64_t rb = lb + s_xl[ui][tid];
+                    const int64_t re = (tid + 1 < un.count) ? lb + s_xl[ui][tid + 1] : le;
+                    const int64_t b = rb > cb ? rb : cb, e = re < ce ? re : ce;
+                    const uint32_t tag = (uint32_t)un.attempt << 24;
+                    for (int64_t pt = b; pt < e; ++pt) {
+                        s_j[pt - p0] = (uint32_t)(un.j0 + tid);
+                        s_s[pt - p0] = tag | (uint32_t)(pt - rb);
+                    }
+                }
+            } else {
+                const uint32_t tag = (uint32_t)un.attempt << 24;
+                for (int64_t pt = cb + tid; pt < ce; pt += BLOCK) {
+                    const uint32_t q = (uint32_t)(pt - lb);
+                    const int i = find_run_smem(s_xl[ui], un.count, q);
+                    s_j[pt - p0] = (uint32_t)(un.j0 + i);
+                    s_s[pt - p0] = tag | (q - s_xl[ui][i]);
+                }
+            }
+        }
+    } else {
+        // many tiny units in one chunk (late attempts of small-k bins): per-point search in global memory
+        for (int l = tid; l < npts; l += BLOCK) {
+            const int64_t pt = p0 + l;
+            const int u = find_unit(p.unit_base, u_lo, u_hi, pt);
+            const g2pc_unit_t un = p.units[u];
+            const uint32_t q = (uint32_t)(pt - __ldg(p.unit_base + u));
+            if (un.attempt < 0) {
+                s_j[l] = (uint32_t)(un.j0 + q);
+                s_s[l] = CENTRE_TAG;
+            } else {
+                const uint32_t* xrow = p.xl + (int64_t)un.attempt * p.n + un.j0;
+                const int i = find_run(xrow, un.count, q);
+                s_j[l] = (uint32_t)(un.j0 + i);
+                s_s[l] = ((uint32_t)un.attempt << 24) | (q - __ldg(xrow + i));
+            }
+        }
     }
     __syncthreads();
-    const int u_lo = s_urange[0], u_hi = s_urange[1];
-
-    const int first = threadIdx.x * PTS_PER_THREAD;
-    if (first < npts) {
-        int64_t pt = p0 + first;
-        int u = find_unit(p.unit_base, u_lo, u_hi, pt);
-        g2pc_unit_t un = p.units[u];
-        int64_t ubase = __ldg(p.unit_base + u), uend = __ldg(p.unit_base + u + 1);
-        const uint32_t* xrow = nullptr;
-        int i = 0;
-        uint32_t s = 0, run_end = 0;
-        bool located = false;
-        const int last = (first + PTS_PER_THREAD < npts) ? first + PTS_PER_THREAD : npts;
-        float4 r0, r1, r2, r3;
-        int64_t jrec = -1;
-        for (int l = first; l < last; ++l, ++pt) {
-            if (pt >= uend) {  // advance to the next non-empty unit
-                u = find_unit(p.unit_base, u + 1, u_hi, pt);
-                un = p.units[u];
-                ubase = __ldg(p.unit_base + u);
-                uend = __ldg(p.unit_base + u + 1);
-                located = false;
-            }
-            const uint32_t q = (uint32_t)(pt - ubase);
-            int64_t j;
-            if (un.attempt < 0) {
-                j = (int64_t)un.j0 + q;
-            } else {
-                if (!located || q >= run_end) {
-                    xrow = p.xl + (int64_t)un.attempt * p.n + un.j0;
-                    i = find_run(xrow, un.count, q);
-                    run_end = (i + 1 < un.count) ? __ldg(xrow + i + 1) : (uint32_t)(uend - ubase);
-                    located = true;
-                }
-                s = q - __ldg(xrow + i);
-                j = (int64_t)un.j0 + i;
-            }
-            if (j != jrec) {
-                const float4* rec = p.records + 4 * j;
-                r0 = __ldg(rec); r1 = __ldg(rec + 1); r2 = __ldg(rec + 2); r3 = __ldg(rec + 3);
-                jrec = j;
-            }
-            float3 x = make_float3(r0.x, r0.y, r0.z);
-            if (un.attempt >= 0) {
-                const float3 e = draw_eps(__float_as_uint(r3.w), s, (uint32_t)un.attempt, p.call_id, p.k0, p.k1);
-                x = mvn_point(x, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, e);
-            }
-            s_xyz[3 * l] = x.x; s_xyz[3 * l + 1] = x.y; s_xyz[3 * l + 2] = x.z;
+    // ---- phase C ----
+    float4 r0[PTS_PER_THREAD], r1[PTS_PER_THREAD];
+    float l22[PTS_PER_THREAD];
+    uint32_t gidv[PTS_PER_THREAD], ss[PTS_PER_THREAD];
+#pragma unroll
+    for (int r = 0; r < PTS_PER_THREAD; ++r) {
+        const int l = tid + r * BLOCK;
+        if (l < npts) {
+            const float4* rec = p.records + 4 * (int64_t)s_j[l];
+            ss[r] = s_s[l];
+            r0[r] = __ldg(rec); r1[r] = __ldg(rec + 1);
+            const float4 r2 = __ldg(rec + 2), r3 = __ldg(rec + 3);
+            l22[r] = r2.x; gidv[r] = __float_as_uint(r3.w);
             s_rgb[3 * l] = r2.y; s_rgb[3 * l + 1] = r2.z; s_rgb[3 * l + 2] = r2.w;
             if (HAS_NRM) { s_nrm[3 * l] = r3.x; s_nrm[3 * l + 1] = r3.y; s_nrm[3 * l + 2] = r3.z; }
+        }
+    }
+    __syncthreads();  // every thread has read its table entries: the xyz staging area may be overwritten
+#pragma unroll
+    for (int r = 0; r < PTS_PER_THREAD; ++r) {
+        const int l = tid + r * BLOCK;
+        if (l < npts) {
+            float3 x = make_float3(r0[r].x, r0[r].y, r0[r].z);
+            if (ss[r] != CENTRE_TAG) {
+                const float3 e = draw_eps(gidv[r], ss[r] & 0x00FFFFFFu, ss[r] >> 24, p.call_id, p.k0, p.k1);
+                x = mvn_point(x, r0[r].w, r1[r].x, r1[r].y, r1[r].z, r1[r].w, l22[r], e);
+            }
+            s_xyz[3 * l] = x.x; s_xyz[3 * l + 1] = x.y; s_xyz[3 * l + 2] = x.z;
         }
     }
     __syncthreads();
@@ -408,8 +484,11 @@ extern "C" int g2pc_sample_count(const float* xyz, const float* cov, const void*
     return G2PC_OK;
 }
 
+extern "C" int g2pc_sample_emit_chunk_points(void) { return TILE_PTS; }
+
 extern "C" int g2pc_sample_emit(const void* records, const uint32_t* xl, int64_t n, const g2pc_unit_t* units,
-                                const int64_t* unit_base, int32_t num_units, uint64_t seed, uint32_t call_id,
+                                const int64_t* unit_base, const int32_t* chunk_unit, int32_t num_units, uint64_t seed,
+                                uint32_t call_id,
                                 float* out_xyz, void* out_rgb, void* out_nrm, int out_dtype, int64_t capacity,
                                 void* stream) {
     G2PC_CHECK_ARG(capacity >= 0 && num_units >= 0, "negative size");
@@ -420,7 +499,7 @@ extern "C" int g2pc_sample_emit(const void* records, const uint32_t* xl, int64_t
                    "outputs must be 16-byte aligned");
     EmitParams p;
     p.records = (const float4*)records; p.xl = xl; p.n = n; p.units = units; p.unit_base = unit_base;
-    p.num_units = num_units; p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32); p.call_id = call_id;
+    p.chunk_unit = chunk_unit; p.num_units = num_units; p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32); p.call_id = call_id;
     p.out_xyz = out_xyz; p.out_rgb = out_rgb; p.out_nrm = out_nrm; p.out_dtype = out_dtype; p.capacity = capacity;
     const unsigned grid = (unsigned)((capacity + TILE_PTS - 1) / TILE_PTS);
     cudaStream_t st = (cudaStream_t)stream;

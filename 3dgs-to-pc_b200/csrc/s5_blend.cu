@@ -9,18 +9,21 @@
 //   Gaussian's running maximum (strict >, over leaves in BFS order and cameras in call order) the maximum and the
 //   blended colour of that pixel are stored (:371-395).
 //
-// Kernel shape: grid = (slabs, leaves); a CTA owns up to 256 quads (4 consecutive pixels of one row) of one leaf and
-// walks the leaf's sorted list in chunks of 128 records staged in shared memory.  Per thread and Gaussian the
+// Kernel shape: grid = (slabs, leaves); a CTA of 128 threads owns up to 128 quads (4 consecutive pixels of one row) of
+// one leaf — a 40x23 leaf is two CTAs, so that the heaviest leaf is no longer the makespan — and walks the leaf's sorted
+// list in chunks of 128 records staged in shared memory.  Leaves are launched heaviest first (leaf_order).  Per thread and Gaussian the
 // row-dependent terms are formed once, then 2 FMA + 1 EX2 + 6 FP32 ops per pixel.  The per-Gaussian maximum is a
 // redux.sync (u32 max of the non-negative float bits) per warp, merged across warps in shared memory and published
 // with ONE 64-bit atomicMax per (CTA, Gaussian): key = (contribution bits << 32) | ~(leaf-pixel index), so ties go to
-// the earliest leaf / lowest pixel, deterministically.  Exact short-cuts only: a warp stops once all its pixels have
-// T below FLT_MIN (every later contribution is then < 1.2e-38).
+// the earliest leaf / lowest pixel, deterministically.  Exact short-cuts only: (i) a warp stops once all its pixels have
+// T below FLT_MIN (every later contribution is then < 1.2e-38); (ii) the arg-max bookkeeping of a Gaussian is skipped
+// by a warp when none of its contributions exceeds the maximum the Gaussian already holds from earlier cameras
+// (the update rule is a strict >, so such contributions can never be recorded).
 #include "colour_common.cuh"
 
 namespace {
 
-constexpr int BT = 256;
+constexpr int BT = 128;
 constexpr int CH = 128;
 constexpr unsigned FULLM = 0xffffffffu;
 
@@ -30,6 +33,7 @@ struct BlendParams {
     const uint32_t* inst_gid;
     const float4* proj;
     unsigned long long* cam_best;
+    const float* max_contrib;  // running per-Gaussian maxima of the earlier cameras (threshold for the bookkeeping)
     float* leaf_colour;
     uint32_t* owner;
     int32_t W, H;
@@ -42,10 +46,10 @@ __device__ __forceinline__ float ex2f(float x) {
     return r;
 }
 
-__global__ void __launch_bounds__(BT) blend_kernel(const BlendParams p) {
+__global__ void __launch_bounds__(BT, 10) blend_kernel(const BlendParams p) {
     __shared__ float4 s_q0[CH];
     __shared__ float4 s_q1[CH];
-    __shared__ float s_b[CH];
+    __shared__ float2 s_b[CH];  // (blue, threshold)
     __shared__ uint32_t s_gid[CH];
     __shared__ unsigned long long s_best[BT / 32][CH];
 
@@ -81,7 +85,7 @@ __global__ void __launch_bounds__(BT) blend_kernel(const BlendParams p) {
             const float4* rec = p.proj + 3 * (int64_t)gid;
             s_q0[tid] = __ldg(rec);
             s_q1[tid] = __ldg(rec + 1);
-            s_b[tid] = __ldg(reinterpret_cast<const float*>(rec + 2));
+            s_b[tid] = make_float2(__ldg(reinterpret_cast<const float*>(rec + 2)), __ldg(p.max_contrib + gid));
             s_gid[tid] = gid;
         }
         __syncthreads();
@@ -89,7 +93,8 @@ __global__ void __launch_bounds__(BT) blend_kernel(const BlendParams p) {
             for (int j = 0; j < nload; ++j) {
                 const float4 q0 = s_q0[j];
                 const float4 q1 = s_q1[j];
-                const float bl = s_b[j];
+                const float2 bt = s_b[j];
+                const float bl = bt.x;
                 const float dy = py - q0.y;
                 const float Bq = dy * q0.w;
                 const float Cq = fmaf(dy * dy, q1.x, q1.y);  // + log2(opacity): alpha = min(0.99, exp2(e))
@@ -105,14 +110,19 @@ __global__ void __launch_bounds__(BT) blend_kernel(const BlendParams p) {
                     Cb[i] = fmaf(c[i], bl, Cb[i]);
                     T[i] -= c[i];
                 }
-                // warp max of the (non-negative) contributions, then the lowest pixel index among the lanes holding it
+                // arg-max bookkeeping only if some contribution can beat what the Gaussian already holds
                 const float v = fmaxf(fmaxf(c[0], c[1]), fmaxf(c[2], c[3]));
-                const uint32_t vb = __float_as_uint(v);
-                const uint32_t wm = __reduce_max_sync(FULLM, vb);
-                const int i = (c[0] == v) ? 0 : (c[1] == v) ? 1 : (c[2] == v) ? 2 : 3;
-                const uint32_t pk = (vb == wm) ? (0xFFFFFFFFu - (uint32_t)(pix_row + i)) : 0u;
-                const uint32_t wp = __reduce_max_sync(FULLM, pk);
-                if (lane == 0) s_best[warp][j] = wm ? (((unsigned long long)wm << 32) | (unsigned long long)wp) : 0ull;
+                if (__any_sync(FULLM, v > bt.y)) {
+                    // warp max of the (non-negative) contributions, then the lowest pixel index among the lanes holding it
+                    const uint32_t vb = __float_as_uint(v);
+                    const uint32_t wm = __reduce_max_sync(FULLM, vb);
+                    const int i = (c[0] == v) ? 0 : (c[1] == v) ? 1 : (c[2] == v) ? 2 : 3;
+                    const uint32_t pk = (vb == wm) ? (0xFFFFFFFFu - (uint32_t)(pix_row + i)) : 0u;
+                    const uint32_t wp = __reduce_max_sync(FULLM, pk);
+                    if (lane == 0) s_best[warp][j] = ((unsigned long long)wm << 32) | (unsigned long long)wp;
+                } else if (lane == 0) {
+                    s_best[warp][j] = 0ull;
+                }
             }
             const float tmax = fmaxf(fmaxf(T[0], T[1]), fmaxf(T[2], T[3]));
             warp_done = __all_sync(FULLM, tmax < 1.17549435e-38f);
@@ -191,15 +201,17 @@ __global__ void __launch_bounds__(256) compose_kernel(uint32_t* __restrict__ own
 
 extern "C" int g2pc_blend(const g2pc_leaf_t* leaves, const int32_t* leaf_order, int32_t num_leaves,
                           int32_t max_leaf_pixels_quads, const uint32_t* inst_gid, const void* proj,
-                          uint64_t* cam_best, float* leaf_colour, uint32_t* owner, int32_t width, int32_t height,
-                          float background, void* stream) {
+                          uint64_t* cam_best, const float* max_contrib, float* leaf_colour, uint32_t* owner,
+                          int32_t width, int32_t height, float background, void* stream) {
     G2PC_CHECK_ARG(num_leaves >= 0, "negative size");
     if (num_leaves == 0) return G2PC_OK;
-    G2PC_CHECK_ARG(leaves && leaf_order && inst_gid && proj && cam_best && leaf_colour && owner, "null pointer");
+    G2PC_CHECK_ARG(leaves && leaf_order && inst_gid && proj && cam_best && max_contrib && leaf_colour && owner,
+                   "null pointer");
     G2PC_CHECK_ARG(max_leaf_pixels_quads >= 1, "max_leaf_pixels_quads < 1");
     BlendParams p;
     p.leaves = leaves; p.leaf_order = leaf_order; p.inst_gid = inst_gid; p.proj = (const float4*)proj;
-    p.cam_best = (unsigned long long*)cam_best; p.leaf_colour = leaf_colour; p.owner = owner;
+    p.cam_best = (unsigned long long*)cam_best; p.max_contrib = max_contrib; p.leaf_colour = leaf_colour;
+    p.owner = owner;
     p.W = width; p.H = height; p.bg = background;
     const unsigned slabs = (unsigned)((max_leaf_pixels_quads + BT - 1) / BT);
     G2PC_CHECK_ARG(num_leaves <= 65535, "too many leaves for one launch");

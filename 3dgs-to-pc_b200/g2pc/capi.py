@@ -30,7 +30,8 @@ SIGNATURES = {
     "g2pc_sample_count": ([_c_void_p, _c_void_p, _c_void_p, ctypes.c_int, _c_void_p, _c_void_p, _c_void_p, _i64, _i64,
                            _c_void_p, _i32, _i32, _i32, _f32, _i32, _u64, _u32, _c_void_p, _c_void_p, _c_void_p,
                            _c_void_p, _c_void_p], ctypes.c_int),
-    "g2pc_sample_emit": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _i32, _u64, _u32, _c_void_p,
+    "g2pc_sample_emit_chunk_points": ([], ctypes.c_int),
+    "g2pc_sample_emit": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p, _i32, _u64, _u32, _c_void_p,
                           _c_void_p, _c_void_p, ctypes.c_int, _i64, _c_void_p], ctypes.c_int),
     "g2pc_dump_eps": ([_c_void_p, _i64, _i32, _i32, _u64, _u32, _c_void_p, _c_void_p], ctypes.c_int),
     "g2pc_preprocess": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i32, _i32, _i64, _c_void_p, _c_void_p,
@@ -44,8 +45,8 @@ SIGNATURES = {
     "g2pc_sort_instances_workspace_bytes": ([_i64], ctypes.c_int64),
     "g2pc_sort_instances": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _i64, _i32, _c_void_p, _i64, _c_void_p,
                              _c_void_p], ctypes.c_int),
-    "g2pc_blend": ([_c_void_p, _c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i32, _i32,
-                    _f32, _c_void_p], ctypes.c_int),
+    "g2pc_blend": ([_c_void_p, _c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                    _i32, _i32, _f32, _c_void_p], ctypes.c_int),
     "g2pc_accumulate": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
     "g2pc_compose_image": ([_c_void_p, _c_void_p, _i32, _i32, _f32, _c_void_p, _c_void_p], ctypes.c_int),
 }
@@ -90,7 +91,7 @@ def load(path=None):
 # ---- launch accounting (bench.py reads these) -------------------------------------------------------------------
 LAUNCHES = 0      # number of g2pc kernel entry points invoked since the last reset
 TIMING = None     # None, or {entry point name: [(start_event, end_event), ...]} to time launches with CUDA events
-_NOT_KERNELS = {"g2pc_version", "g2pc_last_error"}
+_NOT_KERNELS = {"g2pc_version", "g2pc_last_error", "g2pc_sample_emit_chunk_points"}
 
 
 def call(name, *args):

@@ -176,6 +176,11 @@ def run_plan(plan, xyz, cov, colours, normals, perm, num_attempts, std, seed, ca
         capi.ptr(tile_totals), capi.ptr(status), st)
 
     lens = torch.cat([tile_totals[: nt * A].to(torch.int64), centre_d])[src_d]
+    # drop the empty units (later attempts of finished tiles) without a host sync: fixed-size nonzero, padding at the end
+    if nu:
+        nz = torch.nonzero_static(lens, size=nu, fill_value=nu).squeeze(1)
+        lens = torch.cat([lens, lens.new_zeros(1)])[nz]
+        units_d = torch.cat([units_d, units_d.new_zeros((1, 4))])[nz]
     unit_base = torch.zeros((nu + 1,), dtype=torch.int64, device=dev)
     if nu:
         torch.cumsum(lens, 0, out=unit_base[1:])
@@ -185,9 +190,15 @@ def run_plan(plan, xyz, cov, colours, normals, perm, num_attempts, std, seed, ca
     rgb = torch.empty((max(cap, 1), 3), dtype=out_dtype, device=dev)
     nrm = torch.empty((max(cap, 1), 3), dtype=out_dtype, device=dev) if (want_normals and normals is not None) else None
 
-    capi.call("g2pc_sample_emit", capi.ptr(records), capi.ptr(xl), n, capi.ptr(units_d), capi.ptr(unit_base), nu,
-        int(seed) & 0xFFFFFFFFFFFFFFFF, int(call_id) & 0xFFFFFFFF, capi.ptr(pts), capi.ptr(rgb), capi.ptr(nrm),
-        capi.dtype_code(rgb), cap, st)
+    # unit of every output chunk (one vectorised binary search instead of one per CTA)
+    chunk = lib.g2pc_sample_emit_chunk_points()
+    nchunks = (cap + chunk - 1) // chunk
+    starts = torch.arange(nchunks + 1, dtype=torch.int64, device=dev) * chunk
+    chunk_unit = (torch.searchsorted(unit_base, starts, right=True) - 1).clamp_(0, max(nu - 1, 0)).to(torch.int32)
+
+    capi.call("g2pc_sample_emit", capi.ptr(records), capi.ptr(xl), n, capi.ptr(units_d), capi.ptr(unit_base),
+              capi.ptr(chunk_unit), nu, int(seed) & 0xFFFFFFFFFFFFFFFF, int(call_id) & 0xFFFFFFFF, capi.ptr(pts),
+              capi.ptr(rgb), capi.ptr(nrm), capi.dtype_code(rgb), cap, st)
     return pts, rgb, nrm, unit_base[nu], status, (records, xl, tile_totals, unit_base)
 
 

@@ -219,8 +219,8 @@ class GaussPythonRenderer():
             sorted_gid = self._inst_gid_alt if in_alt.value else self._inst_gid
             self._last_sorted_gid = sorted_gid
             capi.call("g2pc_blend", capi.ptr(t["leaves"]), capi.ptr(t["leaf_order"]), num_leaves, t["max_quads"],
-                      capi.ptr(sorted_gid), capi.ptr(self._proj), capi.ptr(self._cam_best), capi.ptr(leaf_colour),
-                      capi.ptr(t["owner"]), W, H, bg, st)
+                      capi.ptr(sorted_gid), capi.ptr(self._proj), capi.ptr(self._cam_best),
+                      capi.ptr(self.gaussian_max_contribution), capi.ptr(leaf_colour), capi.ptr(t["owner"]), W, H, bg, st)
             capi.call("g2pc_accumulate", capi.ptr(self._cam_best), capi.ptr(leaf_colour), n,
                       capi.ptr(self.gaussian_max_contribution), capi.ptr(self.gaussian_colours), st)
             if self.compose_image:

@@ -112,9 +112,13 @@ int g2pc_sample_count(const float* xyz, const float* cov, const void* colours, i
  * caller from tile_totals); inside a sample unit the Gaussian and sample index come from a search of xl;
  * eps is regenerated from the counter and x = mu + L*eps written ("first m samples of the block",
  * gauss_to_pc.py:247-258).  Outputs: out_xyz (capacity,3) f32; out_rgb / out_nrm (capacity,3) in out_dtype
- * (out_nrm may be NULL).  The launch covers `capacity` points; threads beyond unit_base[num_units] exit. */
+ * (out_nrm may be NULL).  The launch covers `capacity` points in chunks of C = g2pc_sample_emit_chunk_points();
+ * threads beyond unit_base[num_units] exit.  chunk_unit (optional, ceil(capacity/C)+1 int32): index of the unit holding
+ * output point c*C (last u with unit_base[u] <= c*C, clamped to num_units - 1) — saves the per-CTA search. */
+int g2pc_sample_emit_chunk_points(void); /* output points per CTA of g2pc_sample_emit (chunk size of chunk_unit) */
 int g2pc_sample_emit(const void* records, const uint32_t* xl, int64_t n, const g2pc_unit_t* units,
-                     const int64_t* unit_base, int32_t num_units, uint64_t seed, uint32_t call_id,
+                     const int64_t* unit_base, const int32_t* chunk_unit, int32_t num_units, uint64_t seed,
+                     uint32_t call_id,
                      float* out_xyz, void* out_rgb, void* out_nrm, int out_dtype, int64_t capacity,
                      void* stream);
 
@@ -204,11 +208,13 @@ int g2pc_sort_instances(uint32_t* inst_leaf, uint32_t* inst_leaf_alt, uint32_t* 
 
 /* S5.  Front-to-back blend of every leaf (gauss_render.py:337-369) + per-Gaussian maximum contribution / arg-max pixel
  * (:371-385) published as cam_best[g] = max((bits(contribution) << 32) | ~leaf_pixel_index).
- * max_leaf_pixels_quads: upper bound of ceil(w/4)*h over the leaves.  leaf_colour: (total_pix,3) f32.
+ * max_leaf_pixels_quads: upper bound of ceil(w/4)*h over the leaves.  max_contrib (n) f32: the running maxima of the
+ * earlier cameras (read-only here; contributions that cannot beat them skip the bookkeeping).  leaf_colour:
+ * (total_pix,3) f32.
  * owner: uint32 per image pixel (zero-filled): 1 + index of the last leaf pixel covering it. */
 int g2pc_blend(const g2pc_leaf_t* leaves, const int32_t* leaf_order, int32_t num_leaves, int32_t max_leaf_pixels_quads,
-               const uint32_t* inst_gid, const void* proj, uint64_t* cam_best, float* leaf_colour, uint32_t* owner,
-               int32_t width, int32_t height, float background, void* stream);
+               const uint32_t* inst_gid, const void* proj, uint64_t* cam_best, const float* max_contrib,
+               float* leaf_colour, uint32_t* owner, int32_t width, int32_t height, float background, void* stream);
 
 /* S6.  Fold one camera into the per-Gaussian accumulators (gauss_render.py:387-395; the role of
  * GaussianRasterizer.update_max_contributions, gaussian_pointcloud_rasterization/__init__.py:142-152):
