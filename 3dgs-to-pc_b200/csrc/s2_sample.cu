@@ -243,8 +243,6 @@ struct EmitParams {
     int64_t capacity;
 };
 
-constexpr int PTS_PER_THREAD = 2;
-constexpr int TILE_PTS = BLOCK * PTS_PER_THREAD;  // 512 output points per CTA
 
 // last u in [lo, hi] with unit_base[u] <= p   (unit_base non-decreasing; zero-length units are skipped over)
 __device__ __forceinline__ int find_unit(const int64_t* __restrict__ base, int lo, int hi, int64_t p) {
@@ -265,7 +263,7 @@ __device__ __forceinline__ int find_run(const uint32_t* __restrict__ xl, int cou
     return lo;
 }
 
-template <typename OUT_T>
+template <typename OUT_T, int TILE_PTS, int BLOCK>
 __device__ __forceinline__ void flush_tile(const float* s, OUT_T* out, int64_t p0, int npts, bool full) {
     if (out == nullptr) return;
     OUT_T* o = out + p0 * 3;
@@ -290,7 +288,7 @@ __device__ __forceinline__ void flush_tile(const float* s, OUT_T* out, int64_t p
     for (int i = threadIdx.x; i < npts * 3; i += BLOCK) o[i] = (OUT_T)s[i];
 }
 
-constexpr int NU_STAGE = 8;  // units whose descriptors / prefix rows are staged in shared memory per chunk
+constexpr int NU_STAGE = 4;  // units whose descriptors / prefix rows are staged in shared memory per chunk
 
 // last i in [0, count) with xs[i] <= q, xs in shared memory
 __device__ __forceinline__ int find_run_smem(const uint32_t* xs, int count, uint32_t q) {
@@ -310,23 +308,30 @@ constexpr uint32_t CENTRE_TAG = 0xFF000000u;
 //      at all), one thread per point with a shared-memory binary search for large k;
 //   C  uniform, divergence-free generation: thread t handles points t and t+256 (independent record
 //      loads in flight, conflict-free staging), then 16-byte coalesced stores.
+constexpr int EPTS = 4;           // points per thread
+constexpr int ETILE = 64 * EPTS;  // output points per emit CTA
+constexpr int EB = 64;            // threads per emit CTA (2 warps: barriers are cheap, many CTAs overlap per SM)
+constexpr int MAX_TILE_G = 256;   // Gaussians per tile (rows of xl staged per unit)
+
 template <typename OUT_T, bool HAS_NRM>
-__global__ void __launch_bounds__(BLOCK, 6) sample_emit_kernel(const EmitParams p) {
-    __shared__ __align__(16) float s_xyz[TILE_PTS * 3];
-    __shared__ __align__(16) float s_rgb[TILE_PTS * 3];
-    __shared__ __align__(16) float s_nrm[HAS_NRM ? TILE_PTS * 3 : 4];
+__global__ void __launch_bounds__(EB, 16) sample_emit_kernel(const EmitParams p) {
+    __shared__ __align__(16) float s_xyz[ETILE * 3];
+    __shared__ __align__(16) float s_rgb[ETILE * 3];
+    __shared__ __align__(16) float s_nrm[HAS_NRM ? ETILE * 3 : 4];
     // the per-point table lives in the xyz staging area: it is dead before the positions are written (barrier below)
     uint32_t* s_j = reinterpret_cast<uint32_t*>(s_xyz);
-    uint32_t* s_s = s_j + TILE_PTS;
+    uint32_t* s_s = s_j + ETILE;
     __shared__ int s_urange[2];
-    __shared__ int64_t s_ubase[NU_STAGE + 1];
+    __shared__ int s_nlong;
+    __shared__ int4 s_long[ETILE / 8];  // runs covering more than 8 points of the chunk (at most TILE_PTS/9 of them)
+    __shared__ int s_urel[NU_STAGE + 1];
     __shared__ g2pc_unit_t s_units[NU_STAGE];
-    __shared__ uint32_t s_xl[NU_STAGE][BLOCK];
+    __shared__ uint32_t s_xl[NU_STAGE][MAX_TILE_G];
 
     const int64_t total = __ldg(p.unit_base + p.num_units);
-    const int64_t p0 = (int64_t)blockIdx.x * TILE_PTS;
+    const int64_t p0 = (int64_t)blockIdx.x * ETILE;
     if (p0 >= total) return;
-    const int64_t pend = (p0 + TILE_PTS < total) ? p0 + TILE_PTS : total;
+    const int64_t pend = (p0 + ETILE < total) ? p0 + ETILE : total;
     const int npts = (int)(pend - p0);
     const int tid = threadIdx.x;
 
@@ -345,51 +350,67 @@ __global__ void __launch_bounds__(BLOCK, 6) sample_emit_kernel(const EmitParams 
     }
     const int nu = u_hi - u_lo + 1;
     if (nu <= NU_STAGE) {  // uniform per CTA
-        // ---- phase A ----
-        if (tid <= nu) s_ubase[tid] = __ldg(p.unit_base + u_lo + tid);
+        // ---- phase A ----  (unit bases become 32-bit offsets relative to the chunk start, clamped to the chunk)
+        if (tid == 0) s_nlong = 0;
+        if (tid <= nu) {
+            const int64_t b = __ldg(p.unit_base + u_lo + tid) - p0;
+            s_urel[tid] = (int)(b < -0x3fffffff ? -0x3fffffff : (b > 0x3fffffff ? 0x3fffffff : b));
+        }
         if (tid < nu) s_units[tid] = p.units[u_lo + tid];
         __syncthreads();
         for (int ui = 0; ui < nu; ++ui) {
             const g2pc_unit_t un = s_units[ui];
-            if (un.attempt >= 0 && tid < un.count)
-                s_xl[ui][tid] = __ldg(p.xl + (int64_t)un.attempt * p.n + un.j0 + tid);
+            if (un.attempt >= 0)
+                for (int e = tid; e < un.count; e += EB)
+                    s_xl[ui][e] = __ldg(p.xl + (int64_t)un.attempt * p.n + un.j0 + e);
         }
         __syncthreads();
         // ---- phase B ----
         for (int ui = 0; ui < nu; ++ui) {
             const g2pc_unit_t un = s_units[ui];
-            const int64_t lb = s_ubase[ui], le = s_ubase[ui + 1];
-            const int64_t cb = lb > p0 ? lb : p0, ce = le < pend ? le : pend;
+            const int lb = s_urel[ui], le = s_urel[ui + 1];  // unit's point range relative to p0 (may be negative)
+            const int cb = lb > 0 ? lb : 0, ce = le < npts ? le : npts;
             if (ce <= cb) continue;
             if (un.attempt < 0) {
-                for (int64_t pt = cb + tid; pt < ce; pt += BLOCK) {
-                    s_j[pt - p0] = (uint32_t)(un.j0 + (pt - lb));
-                    s_s[pt - p0] = CENTRE_TAG;
+                for (int l = cb + tid; l < ce; l += EB) {
+                    s_j[l] = (uint32_t)(un.j0 + (l - lb));
+                    s_s[l] = CENTRE_TAG;
                 }
-            } else if (un.k <= 16) {
-                if (tid < un.count) {
-                    const int64_t rb = lb + s_xl[ui][tid];
-                    const int64_t re = (tid + 1 < un.count) ? lb + s_xl[ui][tid + 1] : le;
-                    const int64_t b = rb > cb ? rb : cb, e = re < ce ? re : ce;
-                    const uint32_t tag = (uint32_t)un.attempt << 24;
-                    for (int64_t pt = b; pt < e; ++pt) {
-                        s_j[pt - p0] = (uint32_t)(un.j0 + tid);
-                        s_s[pt - p0] = tag | (uint32_t)(pt - rb);
+            } else for (int ri = tid; ri < un.count; ri += EB) {
+                // one thread per run: short overlaps are written by the thread itself, long ones are queued and
+                // filled by whole warps (lanes = consecutive points) after the barrier.  lb > -2^30 whenever the unit
+                // overlaps the chunk and a unit holds < 2^30 points, so the 32-bit sums below cannot overflow.
+                const int rb = lb + (int)s_xl[ui][ri];
+                const int re = (ri + 1 < un.count) ? lb + (int)s_xl[ui][ri + 1] : le;
+                if (rb >= ce) break;   // runs are ordered: nothing further overlaps the chunk
+                const int b = rb > cb ? rb : cb, e = re < ce ? re : ce;
+                const uint32_t tag = (uint32_t)un.attempt << 24;
+                if (e - b > 8) {
+                    const int slot = atomicAdd(&s_nlong, 1);
+                    s_long[slot] = make_int4(b, e, un.j0 + ri, (int)(tag | (uint32_t)(b - rb)));
+                } else {
+                    for (int l = b; l < e; ++l) {
+                        s_j[l] = (uint32_t)(un.j0 + ri);
+                        s_s[l] = tag | (uint32_t)(l - rb);
                     }
                 }
-            } else {
-                const uint32_t tag = (uint32_t)un.attempt << 24;
-                for (int64_t pt = cb + tid; pt < ce; pt += BLOCK) {
-                    const uint32_t q = (uint32_t)(pt - lb);
-                    const int i = find_run_smem(s_xl[ui], un.count, q);
-                    s_j[pt - p0] = (uint32_t)(un.j0 + i);
-                    s_s[pt - p0] = tag | (q - s_xl[ui][i]);
+            }
+        }
+        __syncthreads();
+        {
+            const int nlong = s_nlong;
+            const int lane = tid & 31, warp = tid >> 5;
+            for (int r = warp; r < nlong; r += EB / 32) {
+                const int4 d = s_long[r];  // (begin, end, record, tag | first sample)
+                for (int l = d.x + lane; l < d.y; l += 32) {
+                    s_j[l] = (uint32_t)d.z;
+                    s_s[l] = (uint32_t)d.w + (uint32_t)(l - d.x);
                 }
             }
         }
     } else {
         // many tiny units in one chunk (late attempts of small-k bins): per-point search in global memory
-        for (int l = tid; l < npts; l += BLOCK) {
+        for (int l = tid; l < npts; l += EB) {
             const int64_t pt = p0 + l;
             const int u = find_unit(p.unit_base, u_lo, u_hi, pt);
             const g2pc_unit_t un = p.units[u];
@@ -407,12 +428,12 @@ __global__ void __launch_bounds__(BLOCK, 6) sample_emit_kernel(const EmitParams 
     }
     __syncthreads();
     // ---- phase C ----
-    float4 r0[PTS_PER_THREAD], r1[PTS_PER_THREAD];
-    float l22[PTS_PER_THREAD];
-    uint32_t gidv[PTS_PER_THREAD], ss[PTS_PER_THREAD];
+    float4 r0[EPTS], r1[EPTS];
+    float l22[EPTS];
+    uint32_t gidv[EPTS], ss[EPTS];
 #pragma unroll
-    for (int r = 0; r < PTS_PER_THREAD; ++r) {
-        const int l = tid + r * BLOCK;
+    for (int r = 0; r < EPTS; ++r) {
+        const int l = tid + r * EB;
         if (l < npts) {
             const float4* rec = p.records + 4 * (int64_t)s_j[l];
             ss[r] = s_s[l];
@@ -425,8 +446,8 @@ __global__ void __launch_bounds__(BLOCK, 6) sample_emit_kernel(const EmitParams 
     }
     __syncthreads();  // every thread has read its table entries: the xyz staging area may be overwritten
 #pragma unroll
-    for (int r = 0; r < PTS_PER_THREAD; ++r) {
-        const int l = tid + r * BLOCK;
+    for (int r = 0; r < EPTS; ++r) {
+        const int l = tid + r * EB;
         if (l < npts) {
             float3 x = make_float3(r0[r].x, r0[r].y, r0[r].z);
             if (ss[r] != CENTRE_TAG) {
@@ -437,10 +458,27 @@ __global__ void __launch_bounds__(BLOCK, 6) sample_emit_kernel(const EmitParams 
         }
     }
     __syncthreads();
-    const bool full = npts == TILE_PTS;
-    flush_tile<float>(s_xyz, p.out_xyz, p0, npts, full);
-    flush_tile<OUT_T>(s_rgb, (OUT_T*)p.out_rgb, p0, npts, full);
-    if (HAS_NRM) flush_tile<OUT_T>(s_nrm, (OUT_T*)p.out_nrm, p0, npts, full);
+    if (npts == ETILE && sizeof(OUT_T) == 4) {
+        // full chunk, f32 outputs: one loop of 16-byte stores over the three staging areas (they are contiguous)
+        constexpr int V = ETILE * 3 / 4;
+        const float4* sx = reinterpret_cast<const float4*>(s_xyz);
+        const float4* sr = reinterpret_cast<const float4*>(s_rgb);
+        const float4* sn = reinterpret_cast<const float4*>(s_nrm);
+        float4* ox = reinterpret_cast<float4*>(p.out_xyz + p0 * 3);
+        float4* orgb = reinterpret_cast<float4*>((float*)p.out_rgb + p0 * 3);
+        float4* on = HAS_NRM ? reinterpret_cast<float4*>((float*)p.out_nrm + p0 * 3) : nullptr;
+#pragma unroll
+        for (int k = tid; k < V; k += EB) {
+            ox[k] = sx[k];
+            orgb[k] = sr[k];
+            if (HAS_NRM) on[k] = sn[k];
+        }
+    } else {
+        const bool full = npts == ETILE;
+        flush_tile<float, ETILE, EB>(s_xyz, p.out_xyz, p0, npts, full);
+        flush_tile<OUT_T, ETILE, EB>(s_rgb, (OUT_T*)p.out_rgb, p0, npts, full);
+        if (HAS_NRM) flush_tile<OUT_T, ETILE, EB>(s_nrm, (OUT_T*)p.out_nrm, p0, npts, full);
+    }
 }
 
 __global__ void dump_eps_kernel(const int64_t* __restrict__ gids, int64_t n_gids, int32_t k, int32_t attempt,
@@ -484,7 +522,7 @@ extern "C" int g2pc_sample_count(const float* xyz, const float* cov, const void*
     return G2PC_OK;
 }
 
-extern "C" int g2pc_sample_emit_chunk_points(void) { return TILE_PTS; }
+extern "C" int g2pc_sample_emit_chunk_points(void) { return ETILE; }
 
 extern "C" int g2pc_sample_emit(const void* records, const uint32_t* xl, int64_t n, const g2pc_unit_t* units,
                                 const int64_t* unit_base, const int32_t* chunk_unit, int32_t num_units, uint64_t seed,
@@ -501,14 +539,14 @@ extern "C" int g2pc_sample_emit(const void* records, const uint32_t* xl, int64_t
     p.records = (const float4*)records; p.xl = xl; p.n = n; p.units = units; p.unit_base = unit_base;
     p.chunk_unit = chunk_unit; p.num_units = num_units; p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32); p.call_id = call_id;
     p.out_xyz = out_xyz; p.out_rgb = out_rgb; p.out_nrm = out_nrm; p.out_dtype = out_dtype; p.capacity = capacity;
-    const unsigned grid = (unsigned)((capacity + TILE_PTS - 1) / TILE_PTS);
+    const unsigned grid = (unsigned)((capacity + ETILE - 1) / ETILE);
     cudaStream_t st = (cudaStream_t)stream;
     if (out_dtype == G2PC_F32) {
-        if (out_nrm) sample_emit_kernel<float, true><<<grid, BLOCK, 0, st>>>(p);
-        else sample_emit_kernel<float, false><<<grid, BLOCK, 0, st>>>(p);
+        if (out_nrm) sample_emit_kernel<float, true><<<grid, EB, 0, st>>>(p);
+        else sample_emit_kernel<float, false><<<grid, EB, 0, st>>>(p);
     } else {
-        if (out_nrm) sample_emit_kernel<double, true><<<grid, BLOCK, 0, st>>>(p);
-        else sample_emit_kernel<double, false><<<grid, BLOCK, 0, st>>>(p);
+        if (out_nrm) sample_emit_kernel<double, true><<<grid, EB, 0, st>>>(p);
+        else sample_emit_kernel<double, false><<<grid, EB, 0, st>>>(p);
     }
     G2PC_CHECK_LAUNCH();
     return G2PC_OK;

@@ -297,8 +297,14 @@ def cpu_sample_run(wl, n_s, cams_s, threads):
     return o["points"].shape[0], dt, dict(gaussians=n_s, cameras=len(cams), points_requested=points)
 
 
+def host_threads():
+    """Threads for the CPU arm: all cores up to 32 (beyond that the torch-CPU ops of this workload — thousands of
+    small tile tensors — get slower, not faster: measured 240 s at 128 threads vs seconds at 8-32)."""
+    return min(os.cpu_count() or 1, 32)
+
+
 def cpu_baseline(wl, n_s, cams_s):
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     npts, dt, desc = cpu_sample_run(wl, n_s, cams_s, threads)
     return {"value": round(npts / dt / 1e6, 5), "unit": UNIT, "cores": threads, "kind": "port",
             "seconds": round(dt, 2),
@@ -311,7 +317,7 @@ def run_reference(args):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     for _ in range(min(args.warmup, 1)):
         cpu_sample_run(wl, max(2000, args.cpu_sample_gaussians // 10), 1, threads)
     tot_pts, tot_t = 0, 0.0

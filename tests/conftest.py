@@ -11,6 +11,9 @@ for p in (ROOT, PKG):
 
 
 def pytest_configure(config):
+    # the GPU box has >100 host cores: torch-CPU oracle ops on small tensors crawl when oversubscribed
+    import torch
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
