@@ -49,16 +49,20 @@ __device__ __forceinline__ QtTables load_tables(const QtTables g, int n1, int32_
 // starts / ends are non-decreasing within a level, so the candidates form the index range [lo, hi]; nodes inside the
 // range that are dropped or degenerate (e_i <= s_i) are filtered by the caller through axis_member().
 __device__ __forceinline__ void axis_range(const int32_t* __restrict__ s, const int32_t* __restrict__ e, int level,
-                                           float rmin, float rmax, int& lo, int& hi) {
+                                           float rmin, float rmax, float inv_step, int& lo, int& hi) {
     const int n = 1 << level;
     if (!(rmax > rmin)) { lo = 1; hi = 0; return; }
-    // first i with e_i > rmin
-    int a = 0, b = n;
-    while (a < b) { const int m = (a + b) >> 1; if ((float)e[m] > rmin) b = m; else a = m + 1; }
+    // the nodes of a level are (nearly) uniformly spaced: start from the arithmetic guess and walk to the exact answer
+    // (0-2 steps in practice) instead of a binary search.  inv_step = 2^level / extent.
+    // lo = first i with e_i > rmin
+    int a = min(n - 1, max(0, (int)(rmin * inv_step)));
+    while (a < n && !((float)e[a] > rmin)) ++a;
+    while (a > 0 && (float)e[a - 1] > rmin) --a;
     lo = a;
-    // last i with s_i < rmax
-    a = -1; b = n - 1;
-    while (a < b) { const int m = (a + b + 1) >> 1; if ((float)s[m] < rmax) a = m; else b = m - 1; }
+    // hi = last i with s_i < rmax
+    a = min(n - 1, max(0, (int)(rmax * inv_step)));
+    while (a >= 0 && !((float)s[a] < rmax)) --a;
+    while (a + 1 < n && (float)s[a + 1] < rmax) ++a;
     hi = a;
 }
 

@@ -34,7 +34,7 @@ struct PreParams {
     int32_t nodes_2d;     // histogram entries (0: no shared-memory histogram, global atomics)
 };
 
-constexpr int PRE_PER_CTA = 2048;
+constexpr int PRE_PER_CTA = 1024;
 
 __device__ __forceinline__ int off2(int l) { return ((1 << (2 * l)) - 1) / 3; }
 
@@ -85,7 +85,7 @@ __device__ __forceinline__ float3 sh_to_rgb(const float* __restrict__ sh, int st
     return make_float3(out[0], out[1], out[2]);
 }
 
-__global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
+__global__ void __launch_bounds__(256, 4) preprocess_kernel(const PreParams p) {
     extern __shared__ int32_t smem_tab[];
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_tab + 6 * p.n1);
     for (int k = threadIdx.x; k < p.nodes_2d; k += blockDim.x) s_hist[k] = 0u;
@@ -180,12 +180,13 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
         // ---- quadtree membership: flags for nodes that split anyway, exact counts for leaf candidates ----
         float x0, x1, y0, y1;
         gaussian_rect(mx, my, radius, p.cam.width, p.cam.height, x0, x1, y0, y1);
+        const float isx0 = 1.0f / (float)p.cam.width, isy0 = 1.0f / (float)p.cam.height;
         for (int l = 0; l < p.meta.num_levels; ++l) {
             const int o1 = (1 << l) - 1;
             int xlo, xhi, ylo, yhi;
-            axis_range(T.xs + o1, T.xe + o1, l, x0, x1, xlo, xhi);
+            axis_range(T.xs + o1, T.xe + o1, l, x0, x1, isx0 * (float)(1 << l), xlo, xhi);
             if (xlo > xhi) continue;
-            axis_range(T.ys + o1, T.ye + o1, l, y0, y1, ylo, yhi);
+            axis_range(T.ys + o1, T.ye + o1, l, y0, y1, isy0 * (float)(1 << l), ylo, yhi);
             if (ylo > yhi) continue;
             uint32_t* cnt = p.node_cnt + off2(l);
             for (int iy = ylo; iy <= yhi; ++iy) {
@@ -238,6 +239,7 @@ struct EmitParams {
     const int32_t* leaf_of_node;
     uint32_t* inst_leaf;
     uint32_t* inst_gid;
+    uint32_t level_mask;  // bit l set: level l has nodes that are not forced to split (leaf candidates)
 };
 
 __global__ void __launch_bounds__(256) emit_instances_kernel(const EmitParams p) {
@@ -253,12 +255,14 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(const EmitParams p)
     const float4 q0 = p.proj[3 * (int64_t)g];
     float x0, x1, y0, y1;
     gaussian_rect(q0.x, q0.y, q2.z, p.width, p.height, x0, x1, y0, y1);
+    const float isx0 = 1.0f / (float)p.width, isy0 = 1.0f / (float)p.height;
     for (int l = 0; l < p.meta.num_levels; ++l) {
+        if (!((p.level_mask >> l) & 1)) continue;  // no leaf-candidate node at this level
         const int o1 = (1 << l) - 1;
         int xlo, xhi, ylo, yhi;
-        axis_range(T.xs + o1, T.xe + o1, l, x0, x1, xlo, xhi);
+        axis_range(T.xs + o1, T.xe + o1, l, x0, x1, isx0 * (float)(1 << l), xlo, xhi);
         if (xlo > xhi) continue;
-        axis_range(T.ys + o1, T.ye + o1, l, y0, y1, ylo, yhi);
+        axis_range(T.ys + o1, T.ye + o1, l, y0, y1, isy0 * (float)(1 << l), ylo, yhi);
         if (ylo > yhi) continue;
         const int o2 = off2(l);
         for (int iy = ylo; iy <= yhi; ++iy) {
@@ -319,8 +323,9 @@ extern "C" int g2pc_preprocess(const float* xyz, const float* cov, const float* 
 
 extern "C" int g2pc_emit_instances(const void* proj, const uint32_t* order, const uint32_t* incl,
                                    const uint32_t* touched, int64_t n, int32_t width, int32_t height,
-                                   const int32_t* tables, int32_t num_levels, const uint8_t* node_state,
-                                   const int32_t* leaf_of_node, uint32_t* inst_leaf, uint32_t* inst_gid, void* stream) {
+                                   const int32_t* tables, int32_t num_levels, uint32_t level_mask,
+                                   const uint8_t* node_state, const int32_t* leaf_of_node, uint32_t* inst_leaf,
+                                   uint32_t* inst_gid, void* stream) {
     G2PC_CHECK_ARG(n >= 0, "n < 0");
     if (n == 0) return G2PC_OK;
     G2PC_CHECK_ARG(proj && order && incl && touched && tables && node_state && leaf_of_node && inst_leaf && inst_gid,
@@ -333,6 +338,7 @@ extern "C" int g2pc_emit_instances(const void* proj, const uint32_t* order, cons
     p.n1 = (1 << num_levels) - 1;
     p.tab = make_tables(tables, p.n1);
     p.node_state = node_state; p.leaf_of_node = leaf_of_node; p.inst_leaf = inst_leaf; p.inst_gid = inst_gid;
+    p.level_mask = level_mask;
     const size_t smem = (size_t)6 * p.n1 * sizeof(int32_t);
     if (smem > 48 * 1024)
         G2PC_CUDA(cudaFuncSetAttribute(emit_instances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

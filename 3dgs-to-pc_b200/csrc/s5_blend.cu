@@ -12,7 +12,8 @@
 // Kernel shape: grid = (slabs, leaves); a CTA of 128 threads owns up to 128 quads (4 consecutive pixels of one row) of
 // one leaf — a 40x23 leaf is two CTAs, so that the heaviest leaf is no longer the makespan — and walks the leaf's sorted
 // list in chunks of 128 records staged in shared memory.  Leaves are launched heaviest first (leaf_order).  Per thread and Gaussian the
-// row-dependent terms are formed once, then 2 FMA + 1 EX2 + 6 FP32 ops per pixel.  The per-Gaussian maximum is a
+// row-dependent terms are formed once; the per-pixel arithmetic runs on the packed FP32x2 pipe (FADD2 / FFMA2 / FMUL2,
+// two pixels per instruction, scalar broadcast operands): 8 packed ops + 2 EX2 + 2 FMNMX per pixel pair.  The per-Gaussian maximum is a
 // redux.sync (u32 max of the non-negative float bits) per warp, merged across warps in shared memory and published
 // with ONE 64-bit atomicMax per (CTA, Gaussian): key = (contribution bits << 32) | ~(leaf-pixel index), so ties go to
 // the earliest leaf / lowest pixel, deterministically.  Exact short-cuts only: (i) a warp stops once all its pixels have
@@ -38,6 +39,8 @@ struct BlendParams {
     uint32_t* owner;
     int32_t W, H;
     float bg;
+    int32_t* work_counter;  // zero-filled by the caller: dynamic (leaf, slab) work distribution
+    int32_t num_items, slabs;
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -46,31 +49,47 @@ __device__ __forceinline__ float ex2f(float x) {
     return r;
 }
 
-__global__ void __launch_bounds__(BT, 10) blend_kernel(const BlendParams p) {
+__global__ void __launch_bounds__(BT, 9) blend_kernel(const BlendParams p) {
     __shared__ float4 s_q0[CH];
     __shared__ float4 s_q1[CH];
     __shared__ float2 s_b[CH];  // (blue, threshold)
     __shared__ uint32_t s_gid[CH];
     __shared__ unsigned long long s_best[BT / 32][CH];
 
-    const g2pc_leaf_t lf = p.leaves[p.leaf_order[blockIdx.y]];
+    __shared__ int s_item;
+    // persistent CTAs: work items (leaf, slab) are handed out heaviest-leaf-first from a global counter, so the tail of
+    // the launch is at most one item long
+  for (;;) {
+    if (threadIdx.x == 0) s_item = atomicAdd(p.work_counter, 1);
+    __syncthreads();
+    const int item = s_item;
+    __syncthreads();
+    if (item >= p.num_items) break;
+    const g2pc_leaf_t lf = p.leaves[p.leaf_order[item / p.slabs]];
     const int qpr = (lf.w + 3) >> 2;
     const int nquads = qpr * lf.h;
-    const int quad0 = blockIdx.x * BT;
-    if (quad0 >= nquads) return;
+    const int quad0 = (item % p.slabs) * BT;
+    if (quad0 >= nquads) continue;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int quad = quad0 + tid;
     const bool active = quad < nquads;
     const int row = active ? quad / qpr : 0;
     const int x0 = active ? (quad - row * qpr) * 4 : 0;
 
-    float T[4], Cr[4], Cg[4], Cb[4], px[4];
+    // two pixel pairs per thread: Blackwell's packed FP32x2 pipe (FADD2 / FMUL2 / FFMA2) takes a scalar broadcast operand,
+    // so the per-Gaussian scalars feed both pixels of a pair without extra moves
+    float2 T01, T23, px01, px23;
+    float2 Cr01 = make_float2(0.f, 0.f), Cr23 = Cr01, Cg01 = Cr01, Cg23 = Cr01, Cb01 = Cr01, Cb23 = Cr01;
+    {
+        float Tv[4], pxv[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const bool valid = active && (x0 + i < lf.w);
-        T[i] = valid ? 1.0f : 0.0f;  // T = 0 makes every contribution of a padding pixel exactly 0
-        Cr[i] = Cg[i] = Cb[i] = 0.0f;
-        px[i] = (float)(lf.c0 + x0 + i);
+        for (int i = 0; i < 4; ++i) {
+            const bool valid = active && (x0 + i < lf.w);
+            Tv[i] = valid ? 1.0f : 0.0f;  // T = 0 makes every contribution of a padding pixel exactly 0
+            pxv[i] = (float)(lf.c0 + x0 + i);
+        }
+        T01 = make_float2(Tv[0], Tv[1]); T23 = make_float2(Tv[2], Tv[3]);
+        px01 = make_float2(pxv[0], pxv[1]); px23 = make_float2(pxv[2], pxv[3]);
     }
     const float py = (float)(lf.r0 + row);
     const int pix_row = row * lf.w + x0;
@@ -98,18 +117,26 @@ __global__ void __launch_bounds__(BT, 10) blend_kernel(const BlendParams p) {
                 const float dy = py - q0.y;
                 const float Bq = dy * q0.w;
                 const float Cq = fmaf(dy * dy, q1.x, q1.y);  // + log2(opacity): alpha = min(0.99, exp2(e))
-                float c[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float dx = px[i] - q0.x;
-                    const float e = fmaf(dx, fmaf(dx, q0.z, Bq), Cq);
-                    const float a = fminf(0.99f, ex2f(e));
-                    c[i] = T[i] * a;
-                    Cr[i] = fmaf(c[i], q1.z, Cr[i]);
-                    Cg[i] = fmaf(c[i], q1.w, Cg[i]);
-                    Cb[i] = fmaf(c[i], bl, Cb[i]);
-                    T[i] -= c[i];
-                }
+                const float nmx = -q0.x;
+                const float2 dx01 = __fadd2_rn(px01, make_float2(nmx, nmx));
+                const float2 dx23 = __fadd2_rn(px23, make_float2(nmx, nmx));
+                const float2 e01 = __ffma2_rn(dx01, __ffma2_rn(dx01, make_float2(q0.z, q0.z), make_float2(Bq, Bq)),
+                                              make_float2(Cq, Cq));
+                const float2 e23 = __ffma2_rn(dx23, __ffma2_rn(dx23, make_float2(q0.z, q0.z), make_float2(Bq, Bq)),
+                                              make_float2(Cq, Cq));
+                const float2 a01 = make_float2(fminf(0.99f, ex2f(e01.x)), fminf(0.99f, ex2f(e01.y)));
+                const float2 a23 = make_float2(fminf(0.99f, ex2f(e23.x)), fminf(0.99f, ex2f(e23.y)));
+                const float2 c01 = __fmul2_rn(T01, a01);
+                const float2 c23 = __fmul2_rn(T23, a23);
+                Cr01 = __ffma2_rn(c01, make_float2(q1.z, q1.z), Cr01);
+                Cr23 = __ffma2_rn(c23, make_float2(q1.z, q1.z), Cr23);
+                Cg01 = __ffma2_rn(c01, make_float2(q1.w, q1.w), Cg01);
+                Cg23 = __ffma2_rn(c23, make_float2(q1.w, q1.w), Cg23);
+                Cb01 = __ffma2_rn(c01, make_float2(bl, bl), Cb01);
+                Cb23 = __ffma2_rn(c23, make_float2(bl, bl), Cb23);
+                T01 = __ffma2_rn(c01, make_float2(-1.0f, -1.0f), T01);  // T - T*alpha (one rounding)
+                T23 = __ffma2_rn(c23, make_float2(-1.0f, -1.0f), T23);
+                const float c[4] = {c01.x, c01.y, c23.x, c23.y};
                 // arg-max bookkeeping only if some contribution can beat what the Gaussian already holds
                 const float v = fmaxf(fmaxf(c[0], c[1]), fmaxf(c[2], c[3]));
                 if (__any_sync(FULLM, v > bt.y)) {
@@ -124,7 +151,7 @@ __global__ void __launch_bounds__(BT, 10) blend_kernel(const BlendParams p) {
                     s_best[warp][j] = 0ull;
                 }
             }
-            const float tmax = fmaxf(fmaxf(T[0], T[1]), fmaxf(T[2], T[3]));
+            const float tmax = fmaxf(fmaxf(T01.x, T01.y), fmaxf(T23.x, T23.y));
             warp_done = __all_sync(FULLM, tmax < 1.17549435e-38f);
         } else {
             for (int j = lane; j < nload; j += 32) s_best[warp][j] = 0ull;
@@ -148,6 +175,10 @@ __global__ void __launch_bounds__(BT, 10) blend_kernel(const BlendParams p) {
     }
     // final pixel colours: sum + (1 - sum of contributions) * bg; the second factor equals the final T
     if (active) {
+        const float T[4] = {T01.x, T01.y, T23.x, T23.y};
+        const float Cr[4] = {Cr01.x, Cr01.y, Cr23.x, Cr23.y};
+        const float Cg[4] = {Cg01.x, Cg01.y, Cg23.x, Cg23.y};
+        const float Cb[4] = {Cb01.x, Cb01.y, Cb23.x, Cb23.y};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (x0 + i < lf.w) {
@@ -161,6 +192,7 @@ __global__ void __launch_bounds__(BT, 10) blend_kernel(const BlendParams p) {
             }
         }
     }
+  }  // work-item loop
 }
 
 // S6: fold one camera's per-Gaussian winners into the running maxima (strict >, earlier camera wins ties) and fetch
@@ -202,20 +234,26 @@ __global__ void __launch_bounds__(256) compose_kernel(uint32_t* __restrict__ own
 extern "C" int g2pc_blend(const g2pc_leaf_t* leaves, const int32_t* leaf_order, int32_t num_leaves,
                           int32_t max_leaf_pixels_quads, const uint32_t* inst_gid, const void* proj,
                           uint64_t* cam_best, const float* max_contrib, float* leaf_colour, uint32_t* owner,
-                          int32_t width, int32_t height, float background, void* stream) {
+                          int32_t width, int32_t height, float background, int32_t* work_counter, void* stream) {
     G2PC_CHECK_ARG(num_leaves >= 0, "negative size");
     if (num_leaves == 0) return G2PC_OK;
-    G2PC_CHECK_ARG(leaves && leaf_order && inst_gid && proj && cam_best && max_contrib && leaf_colour && owner,
-                   "null pointer");
+    G2PC_CHECK_ARG(leaves && leaf_order && inst_gid && proj && cam_best && max_contrib && leaf_colour && owner &&
+                       work_counter, "null pointer");
     G2PC_CHECK_ARG(max_leaf_pixels_quads >= 1, "max_leaf_pixels_quads < 1");
     BlendParams p;
     p.leaves = leaves; p.leaf_order = leaf_order; p.inst_gid = inst_gid; p.proj = (const float4*)proj;
     p.cam_best = (unsigned long long*)cam_best; p.max_contrib = max_contrib; p.leaf_colour = leaf_colour;
     p.owner = owner;
     p.W = width; p.H = height; p.bg = background;
-    const unsigned slabs = (unsigned)((max_leaf_pixels_quads + BT - 1) / BT);
-    G2PC_CHECK_ARG(num_leaves <= 65535, "too many leaves for one launch");
-    blend_kernel<<<dim3(slabs, (unsigned)num_leaves), BT, 0, (cudaStream_t)stream>>>(p);
+    p.slabs = (max_leaf_pixels_quads + BT - 1) / BT;
+    p.num_items = num_leaves * p.slabs;
+    p.work_counter = work_counter;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int resident = sms * 9;  // __launch_bounds__(BT, 9)
+    const unsigned grid = (unsigned)(p.num_items < resident ? p.num_items : resident);
+    blend_kernel<<<grid, BT, 0, (cudaStream_t)stream>>>(p);
     G2PC_CHECK_LAUNCH();
     return G2PC_OK;
 }

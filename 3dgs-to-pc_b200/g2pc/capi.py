@@ -40,13 +40,13 @@ SIGNATURES = {
     "g2pc_depth_order": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p, _i64, _c_void_p], ctypes.c_int),
     "g2pc_build_tree": ([_c_void_p, _i32, _i32, _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                          _c_void_p, _i32, _c_void_p, _c_void_p], ctypes.c_int),
-    "g2pc_emit_instances": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _i64, _i32, _i32, _c_void_p, _i32, _c_void_p,
-                             _c_void_p, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_emit_instances": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _i64, _i32, _i32, _c_void_p, _i32, _u32,
+                             _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
     "g2pc_sort_instances_workspace_bytes": ([_i64], ctypes.c_int64),
     "g2pc_sort_instances": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _i64, _i32, _c_void_p, _i64, _c_void_p,
                              _c_void_p], ctypes.c_int),
     "g2pc_blend": ([_c_void_p, _c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
-                    _i32, _i32, _f32, _c_void_p], ctypes.c_int),
+                    _i32, _i32, _f32, _c_void_p, _c_void_p], ctypes.c_int),
     "g2pc_accumulate": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
     "g2pc_compose_image": ([_c_void_p, _c_void_p, _i32, _i32, _f32, _c_void_p, _c_void_p], ctypes.c_int),
 }

@@ -83,6 +83,17 @@ class QuadtreeTables:
         return (cat(self.x, "start"), cat(self.x, "end"), cat(self.x, "flags"),
                 cat(self.y, "start"), cat(self.y, "end"), cat(self.y, "flags"))
 
+    def candidate_level_mask(self):
+        """Bit l set iff level l has a live node that is not forced to split by its size (a leaf candidate)."""
+        mask = 0
+        for l in range(self.num_levels):
+            fx, fy = self.x[l]["flags"], self.y[l]["flags"]
+            live_x, live_y = (fx & FLAG_DROPPED) == 0, (fy & FLAG_DROPPED) == 0
+            small_x, small_y = live_x & ((fx & FLAG_BIG) == 0), live_y & ((fy & FLAG_BIG) == 0)
+            if small_x.any() and small_y.any():
+                mask |= 1 << l
+        return mask
+
     def max_leaf_pixels(self):
         return int(min(self.max_tile_size, self.width) * min(self.max_tile_size, self.height))
 

@@ -112,7 +112,7 @@ class GaussPythonRenderer():
             flat = np.concatenate(qt.flat()).astype(np.int32)
             dev = self.device
             t = dict(qt=qt, tables=torch.from_numpy(flat).to(dev),
-                     node_cnt=torch.zeros((qt.nodes_2d,), dtype=torch.int32, device=dev),
+                     node_cnt=torch.zeros((qt.nodes_2d + 1,), dtype=torch.int32, device=dev),
                      node_state=torch.zeros((qt.nodes_2d,), dtype=torch.uint8, device=dev),
                      leaf_of_node=torch.full((qt.nodes_2d,), -1, dtype=torch.int32, device=dev),
                      leaves=torch.zeros((qt.nodes_2d, capi.LEAF_WORDS), dtype=torch.int32, device=dev),
@@ -123,6 +123,7 @@ class GaussPythonRenderer():
                      image=torch.ones((H, W, 3), dtype=torch.float32, device=dev),
                      max_quads=int(max(((int(w) + 3) // 4) * int(h)
                                        for w in [min(self.max_tile_size, W)] for h in [min(self.max_tile_size, H)])))
+            t["work_counter"] = t["node_cnt"][qt.nodes_2d:]  # zeroed together with the node counts
             self._tables[key] = t
         return t
 
@@ -170,7 +171,7 @@ class GaussPythonRenderer():
         while True:
             t = self._get_tables(W, H)
             qt = t["qt"]
-            t["node_cnt"].zero_()
+            t["node_cnt"].zero_()  # (work_counter is the last word of this buffer)
             capi.call("g2pc_preprocess", capi.ptr(self.means3D), capi.ptr(self.cov3d), capi.ptr(self.opacity),
                       capi.ptr(self._colour_f32) if self.shs is None else None, capi.ptr(self.shs),
                       int(self.shs.shape[-1]) if self.shs is not None else 0, self.sh_degree, n, ctypes.byref(cam),
@@ -203,7 +204,7 @@ class GaussPythonRenderer():
                 self._grow(name, total_upper, torch.int32)
             leaf_colour = self._grow("_leaf_colour", total_pix * 3, torch.float32)
             capi.call("g2pc_emit_instances", capi.ptr(self._proj), capi.ptr(self._order), capi.ptr(self._incl),
-                      capi.ptr(self._touched), n, W, H, capi.ptr(t["tables"]), qt.num_levels,
+                      capi.ptr(self._touched), n, W, H, capi.ptr(t["tables"]), qt.num_levels, qt.candidate_level_mask(),
                       capi.ptr(t["node_state"]), capi.ptr(t["leaf_of_node"]), capi.ptr(self._inst_leaf),
                       capi.ptr(self._inst_gid), st)
             ws_bytes = lib.g2pc_sort_instances_workspace_bytes(total_upper)
@@ -220,7 +221,8 @@ class GaussPythonRenderer():
             self._last_sorted_gid = sorted_gid
             capi.call("g2pc_blend", capi.ptr(t["leaves"]), capi.ptr(t["leaf_order"]), num_leaves, t["max_quads"],
                       capi.ptr(sorted_gid), capi.ptr(self._proj), capi.ptr(self._cam_best),
-                      capi.ptr(self.gaussian_max_contribution), capi.ptr(leaf_colour), capi.ptr(t["owner"]), W, H, bg, st)
+                      capi.ptr(self.gaussian_max_contribution), capi.ptr(leaf_colour), capi.ptr(t["owner"]), W, H, bg,
+                      capi.ptr(t["work_counter"]), st)
             capi.call("g2pc_accumulate", capi.ptr(self._cam_best), capi.ptr(leaf_colour), n,
                       capi.ptr(self.gaussian_max_contribution), capi.ptr(self.gaussian_colours), st)
             if self.compose_image:

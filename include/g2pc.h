@@ -192,11 +192,12 @@ int g2pc_build_tree(const int32_t* tables, int32_t num_levels, int32_t max_gauss
                     int32_t max_leaves, int32_t* header, void* stream);
 
 /* S4c.  In depth order: Gaussian order[k] writes (leaf id | 0xFFFFFFFF, Gaussian id) for every leaf-candidate node it
- * overlaps at slots [incl[k] - touched, incl[k]). */
+ * overlaps at slots [incl[k] - touched, incl[k]).  level_mask: bit l set iff level l has nodes that are not forced to
+ * split by their size (levels without leaf candidates are skipped). */
 int g2pc_emit_instances(const void* proj, const uint32_t* order, const uint32_t* incl, const uint32_t* touched,
                         int64_t n, int32_t width, int32_t height, const int32_t* tables, int32_t num_levels,
-                        const uint8_t* node_state, const int32_t* leaf_of_node, uint32_t* inst_leaf,
-                        uint32_t* inst_gid, void* stream);
+                        uint32_t level_mask, const uint8_t* node_state, const int32_t* leaf_of_node,
+                        uint32_t* inst_leaf, uint32_t* inst_gid, void* stream);
 
 /* S4d.  Stable radix sort of the instance pairs on the low leaf_bits bits of the leaf id (cub::DeviceRadixSort): the
  * leaves' lists become contiguous ([seg_begin[l], seg_begin[l+1])) and stay depth-ordered.
@@ -211,10 +212,12 @@ int g2pc_sort_instances(uint32_t* inst_leaf, uint32_t* inst_leaf_alt, uint32_t* 
  * max_leaf_pixels_quads: upper bound of ceil(w/4)*h over the leaves.  max_contrib (n) f32: the running maxima of the
  * earlier cameras (read-only here; contributions that cannot beat them skip the bookkeeping).  leaf_colour:
  * (total_pix,3) f32.
- * owner: uint32 per image pixel (zero-filled): 1 + index of the last leaf pixel covering it. */
+ * owner: uint32 per image pixel (zero-filled): 1 + index of the last leaf pixel covering it.
+ * work_counter: one int32, zero-filled by the caller (persistent CTAs pull (leaf, slab) items, heaviest leaf first). */
 int g2pc_blend(const g2pc_leaf_t* leaves, const int32_t* leaf_order, int32_t num_leaves, int32_t max_leaf_pixels_quads,
                const uint32_t* inst_gid, const void* proj, uint64_t* cam_best, const float* max_contrib,
-               float* leaf_colour, uint32_t* owner, int32_t width, int32_t height, float background, void* stream);
+               float* leaf_colour, uint32_t* owner, int32_t width, int32_t height, float background,
+               int32_t* work_counter, void* stream);
 
 /* S6.  Fold one camera into the per-Gaussian accumulators (gauss_render.py:387-395; the role of
  * GaussianRasterizer.update_max_contributions, gaussian_pointcloud_rasterization/__init__.py:142-152):
