@@ -218,11 +218,16 @@ def run_ours(args):
     n_active = int(getattr(g2p, "LAST_SAMPLE_STATS", {}).get("n_active", 0))
     p_rank = int(pc.points.shape[0])
     alg_bytes = n_active * 44 + p_rank * 36  # 12 mu + 24 Sigma/L + 8 count/offset per Gaussian; 36 B/point
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_emit_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roof = None
     if emit_ms:
         ach = alg_bytes / (emit_ms * 1e-3) / 1e9
         roof = {"kernel": "sample_emit_kernel", "bound": "hbm", "achieved": round(ach, 1), "peak": peak_gbs,
-                "unit": "GB/s", "frac": round(ach / peak_gbs, 4), "traffic": None,
+                "unit": "GB/s", "frac": round(ach / peak_gbs, 4), "traffic": traffic,
                 "peak_source": "measured" if peaks else "fallback", "alg_bytes_per_launch": alg_bytes,
                 "avg_launch_ms": round(emit_ms, 4)}
     kernel_ms = {k.replace("g2pc_", ""): round(float(np.sum(v)) / args.steps, 3) for k, v in timing.items() if v}
