@@ -308,13 +308,13 @@ constexpr uint32_t CENTRE_TAG = 0xFF000000u;
 //      at all), one thread per point with a shared-memory binary search for large k;
 //   C  uniform, divergence-free generation: thread t handles points t and t+256 (independent record
 //      loads in flight, conflict-free staging), then 16-byte coalesced stores.
-constexpr int EPTS = 2;           // points per thread
+constexpr int EPTS = 4;           // points per thread
 constexpr int ETILE = 64 * EPTS;  // output points per emit CTA
 constexpr int EB = 64;            // threads per emit CTA (2 warps: barriers are cheap, many CTAs overlap per SM)
 constexpr int MAX_TILE_G = 256;   // Gaussians per tile (rows of xl staged per unit)
 
 template <typename OUT_T, bool HAS_NRM>
-__global__ void __launch_bounds__(EB, 24) sample_emit_kernel(const EmitParams p) {
+__global__ void __launch_bounds__(EB, 16) sample_emit_kernel(const EmitParams p) {
     __shared__ __align__(16) float s_xyz[ETILE * 3];
     __shared__ __align__(16) float s_rgb[ETILE * 3];
     __shared__ __align__(16) float s_nrm[HAS_NRM ? ETILE * 3 : 4];

@@ -139,3 +139,26 @@ def test_camera_behind_everything_and_empty(lib):
     assert float(img.min()) == 1.0  # white background
     with pytest.raises(NotImplementedError):
         gr.get_renderer("cuda", d["xyz"], d["opacities"].unsqueeze(1), d["colours"], cov)
+
+
+def test_cli_end_to_end(lib, tmp_path):
+    """gauss_to_pc.main() on a synthetic .ply + transforms.json: same flags as the reference CLI."""
+    import gauss_dataloader as gd
+    import gauss_to_pc as g2p
+    from g2pc import synth
+    from test_io_cpu import write_gaussian_ply, write_transforms_json
+    sc = synth.make_scene(3000, seed=21, sh_degree=3)
+    cams, intr = synth.make_cameras(3)
+    ply, tj, out = str(tmp_path / "scene.ply"), str(tmp_path / "transforms.json"), str(tmp_path / "pc.ply")
+    write_gaussian_ply(ply, sc)
+    write_transforms_json(tj, cams, intr)
+    g2p.main(["--input_path", ply, "--transform_path", tj, "--output_path", out, "--renderer_type", "python",
+              "--num_points", "30000", "--colour_quality", "tiny", "--quiet"])
+    v = gd.read_ply_vertices(out)
+    assert abs(v.shape[0] - 30000) < 600
+    assert v.dtype.names == ("x", "y", "z", "nx", "ny", "nz", "red", "green", "blue")
+    assert np.isfinite(np.stack([v["x"], v["y"], v["z"]])).all()
+    assert v["red"].max() > 0
+    # --no_render_colours path (BASELINE config 1 shape)
+    g2p.main(["--input_path", ply, "--output_path", out, "--no_render_colours", "--num_points", "20000", "--quiet"])
+    assert abs(gd.read_ply_vertices(out).shape[0] - 20000) < 400
