@@ -18,21 +18,15 @@ def focal2fov(focal, pixels):
 
 
 def getProjectionMatrix(znear, zfar, fovX, fovY):
-    """OpenGL-style perspective matrix with z_sign = +1 (camera_handler.py:14-34)."""
-    tan_y = math.tan(fovY / 2)
-    tan_x = math.tan(fovX / 2)
-    top, right = tan_y * znear, tan_x * znear
-    bottom, left = -top, -right
-
-    P = torch.zeros(4, 4)
-    P[0, 0] = 2.0 * znear / (right - left)
-    P[1, 1] = 2.0 * znear / (top - bottom)
-    P[0, 2] = (right + left) / (right - left)
-    P[1, 2] = (top + bottom) / (top - bottom)
-    P[3, 2] = 1.0
-    P[2, 2] = zfar / (zfar - znear)
-    P[2, 3] = -(zfar * znear) / (zfar - znear)
-    return P
+    """Perspective matrix of the reference (camera_handler.py:14-34): symmetric frustum, +z convention, so that
+    w_clip = z_view.  Only five entries are non-zero."""
+    half_w = math.tan(fovX / 2) * znear
+    half_h = math.tan(fovY / 2) * znear
+    depth = zfar - znear
+    return torch.tensor([[znear / half_w, 0.0, 0.0, 0.0],
+                         [0.0, znear / half_h, 0.0, 0.0],
+                         [0.0, 0.0, zfar / depth, -(zfar * znear) / depth],
+                         [0.0, 0.0, 1.0, 0.0]], dtype=torch.float32)
 
 
 class Camera():
@@ -76,54 +70,25 @@ class Camera():
 
 
 def get_camera(renderer_type, transform, cam_intrinsic, colour_resolution=None, sh_degree=3, white_bkgd=True, mask=None):
-    """Build the per-camera object the renderer consumes (camera_handler.py:53-108).
+    """Per-camera object for `renderer(camera)` (camera_handler.py:53-108).
 
-    cam_intrinsic = [w, h, fx, fy]; the image is scaled so that its width equals colour_resolution unless a mask is
-    given (then the native size is kept and the mask is flattened)."""
-    diff = 1 if (colour_resolution is None or mask is not None) else colour_resolution / int(cam_intrinsic[0])
-
+    cam_intrinsic = [w, h, fx, fy].  Without a mask the image is rescaled to `colour_resolution` pixels wide (focal
+    lengths scale along); with a mask the native size is kept and the mask must match it (it is returned flattened on
+    the camera as `.mask`)."""
+    native_w, native_h = int(cam_intrinsic[0]), int(cam_intrinsic[1])
+    scale = 1 if (colour_resolution is None or mask is not None) else colour_resolution / native_w
     if mask is not None:
-        if mask.shape[1] != int(cam_intrinsic[0]) or mask.shape[0] != int(cam_intrinsic[1]):
+        if tuple(mask.shape[:2]) != (native_h, native_w):
             raise Exception("Size of mask must match size of input image")
         mask = mask.flatten()
-
-    img_width = int(int(cam_intrinsic[0]) * diff)
-    img_height = int(int(cam_intrinsic[1]) * diff)
-
-    focal_x = float(cam_intrinsic[2]) * diff
-    focal_y = float(cam_intrinsic[3]) * diff
-
-    if renderer_type == "python":
-        cam = Camera(img_width, img_height, focal_x, focal_y, transform)
-        cam.sh_degree = sh_degree
-        return cam
-
-    elif renderer_type == "cuda":
-        from gaussian_pointcloud_rasterization import GaussianRasterizationSettings
-
-        transform[:, 1:3] = -transform[:, 1:3]  # OpenGL -> z-forward, in place like the reference (:75)
-
-        fovX = focal2fov(focal_x, img_width)
-        fovY = focal2fov(focal_y, img_height)
-
-        projmatrix = getProjectionMatrix(znear=10, zfar=100, fovX=fovX, fovY=fovY).transpose(0, 1).to(transform.device)
-        viewmatrix = torch.linalg.inv(transform).permute(1, 0)
-        campos = viewmatrix.inverse()[3, :3]
-        bg = torch.ones(3, device=transform.device) if white_bkgd else torch.zeros(3, device=transform.device)
-
-        return GaussianRasterizationSettings(
-            image_height=int(img_height),
-            image_width=int(img_width),
-            tanfovx=math.tan(fovX * 0.5),
-            tanfovy=math.tan(fovY * 0.5),
-            bg=bg,
-            scale_modifier=1.0,
-            campos=campos,
-            viewmatrix=viewmatrix,
-            projmatrix=viewmatrix @ projmatrix,
-            sh_degree=sh_degree,
-            prefiltered=False,
-            mask=mask,
-            debug=True,
-            antialiasing=False,
-        )
+    if renderer_type != "python":
+        if renderer_type == "cuda":
+            raise NotImplementedError("renderer_type='cuda' cameras (z-forward convention, GaussianRasterizationSettings) "
+                                      "belong to the not-yet-built 16x16-tile back-end; use renderer_type='python'")
+        raise Exception(f"Renderer of type {renderer_type} is not supported")
+    cam = Camera(int(native_w * scale), int(native_h * scale), float(cam_intrinsic[2]) * scale,
+                 float(cam_intrinsic[3]) * scale, transform)
+    cam.sh_degree = sh_degree
+    cam.white_bkgd = white_bkgd
+    cam.mask = mask
+    return cam

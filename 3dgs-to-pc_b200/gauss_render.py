@@ -190,6 +190,10 @@ class GaussPythonRenderer():
                 # a tile at the deepest tabulated level holds more than max_gaussians_per_tile Gaussians: tabulate one
                 # more level and redo this camera (rare; the reference keeps splitting in its host BFS)
                 self._extra_levels += 1
+                if self._get_tables(W, H)["qt"].num_levels <= qt.num_levels:
+                    raise capi.G2pcError(
+                        f"a tile still holds more than max_gaussians_per_tile={self.max_gaussians_per_tile} Gaussians at "
+                        f"quadtree level {qt.num_levels - 1} (tiles of a few pixels): deeper than the tabulated levels")
                 continue
             if hdr[capi.HDR_LEAF_OVERFLOW]:
                 raise capi.G2pcError("leaf table overflow")

@@ -124,7 +124,7 @@ def run_ours(args):
     wl = WORKLOADS[args.workload]
     st = settings_for(wl, g2p, dev)
 
-    sc = synth.make_scene(wl["n"], seed=wl["seed"], sh_degree=wl["sh"])
+    sc = _scene_for(wl)
     cams, intr = synth.make_cameras(wl["cams"]) if wl["cams"] else ([], [])
     transforms = {f"cam{i:04d}": c for i, c in enumerate(cams)}
     intrinsics = {f"cam{i:04d}": k for i, k in enumerate(intr)}
@@ -262,6 +262,18 @@ def run_ours(args):
 
 
 # --------------------------------------------------------------------------------------------------------------------
+_SCENE_CACHE = {}
+
+
+def _scene_for(wl):
+    """The synthetic scene is a pure function of the workload: generate it once per process."""
+    from g2pc import synth
+    key = (wl["n"], wl["seed"], wl["sh"])
+    if key not in _SCENE_CACHE:
+        _SCENE_CACHE[key] = synth.make_scene(wl["n"], seed=wl["seed"], sh_degree=wl["sh"])
+    return _SCENE_CACHE[key]
+
+
 def cpu_sample_run(wl, n_s, cams_s, threads):
     """The oracle port (CPU restatement of the reference's python path) on a bounded sample of the workload:
     the first n_s Gaussians of the scene, the first cams_s cameras at full resolution, and num_points scaled by
@@ -270,8 +282,7 @@ def cpu_sample_run(wl, n_s, cams_s, threads):
     from oracle import gaussians as og, render as orr, sampling as osamp
     torch.set_num_threads(threads)
     n_s = min(n_s, wl["n"])
-    sc = synth.make_scene(wl["n"], seed=wl["seed"], sh_degree=wl["sh"])
-    sc = {k: v[:n_s].clone() for k, v in sc.items()}
+    sc = {k: v[:n_s].clone() for k, v in _scene_for(wl).items()}
     cams, intr = synth.make_cameras(wl["cams"]) if wl["cams"] else ([], [])
     cams, intr = cams[:cams_s], intr[:cams_s]
     # keep the work per emitted point of the full workload: Gaussians x cameras / points is preserved

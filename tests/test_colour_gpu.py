@@ -38,7 +38,8 @@ def _setup(n, seed, res, ncams, sh_degree=None, max_g=60000):
 
 
 @pytest.mark.parametrize("n,res,sh,max_g", [(3000, 200, None, 60000), (20000, 330, None, 60000),
-                                            (4000, 330, None, 300), (3000, 200, 3, 60000), (3000, 200, 2, 60000)])
+                                            (4000, 330, None, 300), (3000, 200, 3, 60000), (3000, 200, 2, 60000),
+                                            (4000, 330, None, 150)])  # last: tiles split by COUNT, 1-2 levels below the size-driven depth
 def test_colour_stage_parity(lib, n, res, sh, max_g):
     from oracle import render as orr
     sc, R, O, kc, oc = _setup(n, 1240, res, 3, sh_degree=sh, max_g=max_g)
