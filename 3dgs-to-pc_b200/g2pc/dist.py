@@ -138,6 +138,10 @@ def convert_gaussians_to_pc_sharded(scene, transforms, intrinsics, settings, ren
 
     rank, W = world()
     s = settings
+    if s.bounding_box_min is not None or s.bounding_box_max is not None or s.cull_large_percentage > 0.0 or \
+            s.surface_distance_std is not None or s.generate_mesh:
+        raise NotImplementedError("the sharded pipeline covers the visibility / opacity culls only; bounding boxes, "
+                                  "size culls, surface distances and meshing run through convert_gaussians_to_pc")
     n_all = scene["xyz"].shape[0]
     gaussians = Gaussians(scene["xyz"], scene["scales"], scene["rots"], scene["colours"], scene["opacities"],
                           shs=scene.get("shs"))

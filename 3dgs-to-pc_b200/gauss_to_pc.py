@@ -6,9 +6,6 @@ sample_from_multivariate_normal :140, create_new_gaussian_points :157, generate_
 convert_3dgs_to_pc :373).  The sampling stage runs as two fused sm_100a kernels (csrc/s2_sample.cu) driven by
 g2pc/sampler.py; the colour stage runs through gauss_render.get_renderer.  No CPU fallback.
 """
-import gc
-import sys
-from math import floor
 from typing import NamedTuple
 
 import numpy as np

@@ -109,7 +109,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
-    from g2pc import build, capi, config, sampler, synth
+    from g2pc import build, capi, sampler, synth
     build.build()
     capi.load()
     import gauss_to_pc as g2p

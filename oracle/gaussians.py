@@ -5,7 +5,6 @@ library routine (bmm, eigvals, eigh) so that the CPU result has the same roundin
 """
 import math
 
-import numpy as np
 import torch
 
 

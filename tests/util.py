@@ -1,9 +1,7 @@
 """Shared helpers for the parity tests."""
 import os
-import sys
 
 import numpy as np
-import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
