@@ -49,3 +49,16 @@ def test_sass_is_sm100a(lib):
         pytest.skip("cuobjdump not available")
     out = subprocess.run(["cuobjdump", "-lelf", capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under 3dgs-to-pc_b200/ may import or execute it."""
+    pkg = os.path.join(ROOT, "3dgs-to-pc_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M) or "oracle/" in text:
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
