@@ -117,6 +117,8 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # torchrun pins OMP_NUM_THREADS=1: give every rank its share of the host cores for the (untimed) scene synthesis
+    torch.set_num_threads(max(1, min(16, (os.cpu_count() or 1) // world)))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
