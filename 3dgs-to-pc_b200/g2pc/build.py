@@ -37,9 +37,24 @@ def _stale():
 
 
 def build(force=False, verbose=False, extra_flags=()):
-    """Compile every .cu under csrc/ into one shared library.  Returns the library path."""
+    """Compile every .cu under csrc/ into one shared library.  Returns the library path.
+    Safe to call from several processes at once (torchrun ranks): an exclusive file lock serialises the build and the
+    staleness check is repeated under the lock."""
     if not force and not _stale():
         return LIB_PATH
+    import fcntl
+    os.makedirs(os.path.join(PKG_ROOT, "build"), exist_ok=True)
+    with open(os.path.join(PKG_ROOT, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIB_PATH
+            return _build_locked(verbose, extra_flags)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose, extra_flags):
     nvcc = os.environ.get("NVCC", "nvcc")
     objs = []
     procs = []
@@ -58,10 +73,12 @@ def build(force=False, verbose=False, extra_flags=()):
             raise RuntimeError(f"nvcc failed for {src}:\n{out.decode()}")
         if verbose and out:
             print(out.decode())
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-lcudart"]
+    tmp = LIB_PATH + ".tmp"
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-lcudart"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout.decode()}")
+    os.replace(tmp, LIB_PATH)  # atomic: a concurrent loader never sees a half-written library
     return LIB_PATH
 
 
