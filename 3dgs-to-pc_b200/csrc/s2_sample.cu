@@ -10,7 +10,7 @@
 //
 // Pass 1 (sample_count_kernel): one CTA per tile.  Gathers the tile's Gaussians, factors Sigma, packs a 64-byte
 //   record per Gaussian in bin order, simulates the attempt loop and writes per-attempt tile-local prefixes.
-// Pass 2 (sample_emit_kernel): one CTA per 512 OUTPUT points; runs are expanded into a per-point table in shared
+// Pass 2 (sample_emit_kernel): one 64-thread CTA per 256 OUTPUT points; runs are expanded into a per-point table in shared
 //   memory, points are generated divergence-free (4 per thread, strided), staged in shared memory and leave as
 //   16-byte coalesced stores.  RNG is regenerated, never stored.
 #include "common.cuh"
@@ -302,11 +302,11 @@ __device__ __forceinline__ int find_run_smem(const uint32_t* xs, int count, uint
 
 constexpr uint32_t CENTRE_TAG = 0xFF000000u;
 
-// Pass 2, three phases per 512-point chunk:
+// Pass 2, three phases per 256-point chunk (ETILE):
 //   A  stage the descriptors / bases / prefix rows of the (few) units the chunk overlaps in shared memory;
 //   B  expand runs into a per-point (record index, attempt|sample) table: one thread per run for small k (no search
 //      at all), one thread per point with a shared-memory binary search for large k;
-//   C  uniform, divergence-free generation: thread t handles points t and t+256 (independent record
+//   C  uniform, divergence-free generation: thread t handles points t, t+64, t+128, t+192 (independent record
 //      loads in flight, conflict-free staging), then 16-byte coalesced stores.
 constexpr int EPTS = 4;           // points per thread
 constexpr int ETILE = 64 * EPTS;  // output points per emit CTA
