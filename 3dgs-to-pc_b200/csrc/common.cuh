@@ -60,9 +60,10 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
     return o;
 }
 
-// u32 -> uniform in (0,1): ((x >> 8) + 0.5) * 2^-24   (never 0, never 1)
+// u32 -> uniform in (0,1): ((x >> 9) + 0.5) * 2^-23.  x >> 9 < 2^23, so the +0.5 is exact in fp32 and the result lies
+// in [2^-24, 1 - 2^-24]: never 0, never 1.
 __device__ __forceinline__ float u32_to_unit(uint32_t x) {
-    return ((float)(x >> 8) + 0.5f) * 5.9604644775390625e-08f;
+    return ((float)(x >> 9) + 0.5f) * 1.1920928955078125e-07f;
 }
 
 __device__ __forceinline__ float fast_sqrt(float x) {
@@ -77,8 +78,9 @@ __device__ __forceinline__ float3 draw_eps(uint32_t gid, uint32_t sample, uint32
     Philox4 r = philox4x32_10(gid, sample, attempt, call, k0, k1);
     const float TWO_PI = 6.283185307179586f;
     float u1 = u32_to_unit(r.x), u2 = u32_to_unit(r.y), u3 = u32_to_unit(r.z), u4 = u32_to_unit(r.w);
-    float ra = fast_sqrt(-2.0f * __logf(u1));
-    float rb = fast_sqrt(-2.0f * __logf(u3));
+    // the approximate log of u just below 1 may come out slightly positive: clamp before the square root
+    float ra = fast_sqrt(fmaxf(0.0f, -2.0f * __logf(u1)));
+    float rb = fast_sqrt(fmaxf(0.0f, -2.0f * __logf(u3)));
     float sa, ca, cb;
     __sincosf(TWO_PI * u2, &sa, &ca);
     cb = __cosf(TWO_PI * u4);

@@ -505,6 +505,8 @@ extern "C" int g2pc_sample_count(const float* xyz, const float* cov, const void*
     G2PC_CHECK_ARG(colour_dtype == G2PC_F32 || colour_dtype == G2PC_F64, "bad colour_dtype");
     G2PC_CHECK_ARG(num_attempts >= 1 && attempts_stored >= 1 && attempts_stored <= num_attempts,
                    "need 1 <= attempts_stored <= num_attempts");
+    // the emit pass tags every sample with (attempt << 24 | sample); tag 0xFF is the centre-point marker
+    G2PC_CHECK_ARG(attempts_stored <= 255, "attempts_stored must be <= 255 (8-bit attempt tag, 0xFF reserved)");
     G2PC_CHECK_ARG(cull_mode == G2PC_CULL_EPS_NORM || cull_mode == G2PC_CULL_EXPLICIT, "bad cull_mode");
     G2PC_CHECK_ARG(((uintptr_t)records & 15) == 0, "records must be 16-byte aligned");
     CountParams p;

@@ -13,8 +13,9 @@ CULL_MODE = 1
 # (gauss_dataloader.py:176-200); float32 halves the output traffic and leaves the PLY bytes unchanged.
 OUTPUT_DTYPE = torch.float32
 
-# Dense attempts stored by the count pass; attempts beyond this only flag an overflow (re-run with more).
-MAX_ATTEMPTS_STORED = 32
+# Dense attempts the count pass stores on its first try; if a Gaussian still emits in a later attempt the sampler
+# replays the (deterministic) stream with every attempt stored (gauss_to_pc._attempt_ladder).
+ATTEMPTS_STORED_FIRST = 16
 
 # python-renderer tile parameters.  The reference derives them from free GPU memory at call time
 # (gauss_render.py:440-444), which makes results hardware dependent; they are pinned to render()'s own defaults

@@ -95,6 +95,10 @@ class SamplePlan:
     def __init__(self, bin_k_count, attempts_stored, include_centres=True):
         """bin_k_count: list of (k, count) in output order; Gaussians of bin b occupy bin-order indices
         [J0_b, J0_b + count_b)."""
+        if attempts_stored > 255:
+            raise capi.G2pcError("attempts_stored must be <= 255 (8-bit attempt tag of the emit pass)")
+        if any(k >= (1 << 24) for (k, _) in bin_k_count):
+            raise capi.G2pcError("more than 2^24 - 1 samples per Gaussian per attempt (24-bit sample tag of the emit pass)")
         tiles, units, unit_src = [], [], []
         j0 = 0
         tile_base_index = 0

@@ -88,15 +88,30 @@ def calculate_bin_sizes(points_per_gaussian):
     return sampler.calculate_bin_sizes_from_hist(hist[np.nonzero(hist)[0]])
 
 
+def _attempt_ladder(num_attempts):
+    """Stored-attempt sizes to try: most Gaussians finish within a few attempts, so the count pass first keeps
+    config.ATTEMPTS_STORED_FIRST dense attempts; if some Gaussian still emits later (status word ST_OVERFLOW, e.g. a
+    small --mahalanobis_distance_std with --exact_num_points) the deterministic stream is simply replayed with every
+    attempt stored.  The reference has no such limit (gauss_to_pc.py:189-263)."""
+    num_attempts = int(num_attempts)
+    if num_attempts > 255:
+        raise capi.G2pcError("num_sample_attempts must be <= 255 (8-bit attempt tag in the emit pass)")
+    first = min(num_attempts, config.ATTEMPTS_STORED_FIRST)
+    return [first] if first == num_attempts else [first, num_attempts]
+
+
 def _single_bin_run(k, means, covariances, colours, normals, std, num_attempts, include_centres, seed, call_id,
                     out_dtype=None, cull_mode=None):
     n = means.shape[0]
-    A = min(int(num_attempts), config.MAX_ATTEMPTS_STORED)
-    plan = sampler.SamplePlan([(int(k), n)], A, include_centres=include_centres)
     perm = torch.arange(n, dtype=torch.int32, device=means.device)
-    return sampler.run_plan(plan, means.to(torch.float32), covariances.to(torch.float32), colours, normals, perm,
-                            num_attempts, std, seed, call_id, out_dtype=out_dtype, cull_mode=cull_mode,
-                            want_normals=normals is not None)
+    for A in _attempt_ladder(num_attempts):
+        plan = sampler.SamplePlan([(int(k), n)], A, include_centres=include_centres)
+        res = sampler.run_plan(plan, means.to(torch.float32), covariances.to(torch.float32), colours, normals, perm,
+                               num_attempts, std, seed, call_id, out_dtype=out_dtype, cull_mode=cull_mode,
+                               want_normals=normals is not None)
+        if A == num_attempts or not int(res[4][capi.ST_OVERFLOW].item()):
+            break
+    return res
 
 
 def sample_from_multivariate_normal(means, covariances, num_points_to_sample, max_num_gen_attempts=3, epsilon=1e-6):
@@ -130,9 +145,9 @@ def create_new_gaussian_points(num_points_to_sample, means, covariances, colours
 
 def _check_status(status):
     s = status.tolist()
-    if s[capi.ST_OVERFLOW]:
-        raise capi.G2pcError("sampling needed more stored attempts than g2pc.config.MAX_ATTEMPTS_STORED "
-                             f"({config.MAX_ATTEMPTS_STORED}); raise it and re-run")
+    if s[capi.ST_OVERFLOW]:  # cannot happen through the drivers in this module (they replay with every attempt stored)
+        raise capi.G2pcError("the count pass stored fewer attempts than some Gaussian needed; re-run with "
+                             "attempts_stored = num_attempts")
     if s[capi.ST_CHOLFAIL] and not getattr(config, "QUIET_CHOL", False):
         print(f"WARNING: Could not generate points for {s[capi.ST_CHOLFAIL]} Gaussians "
               "(covariance not positive-definite even after regularisation)")
@@ -203,11 +218,15 @@ def sample_points_per_gaussian(xyz, covariances, colours, normals, points_per_ga
     global LAST_SAMPLE_STATS
     LAST_SAMPLE_STATS = {"n_active": n_used, "bins": len(bins)}
 
-    A = min(int(num_sample_attempts), config.MAX_ATTEMPTS_STORED)
-    plan = sampler.SamplePlan([(n - 1, count) for (_, _, n, count) in bins], A, include_centres=True)
-    pts, cols, nrm, total, status, bufs = sampler.run_plan(
-        plan, xyz.to(torch.float32), covariances.to(torch.float32), colours, normals, perm, num_sample_attempts,
-        mahalanobis_distance_std, seed, call_id, gid_offset=gid_offset, want_normals=normals is not None, gids=gids)
+    for A in _attempt_ladder(num_sample_attempts):
+        plan = sampler.SamplePlan([(n - 1, count) for (_, _, n, count) in bins], A, include_centres=True)
+        pts, cols, nrm, total, status, bufs = sampler.run_plan(
+            plan, xyz.to(torch.float32), covariances.to(torch.float32), colours, normals, perm, num_sample_attempts,
+            mahalanobis_distance_std, seed, call_id, gid_offset=gid_offset, want_normals=normals is not None,
+            gids=gids)
+        # (the overflow word is read only when a replay is possible; callers sync on `total` right after anyway)
+        if A == int(num_sample_attempts) or not int(status[capi.ST_OVERFLOW].item()):
+            break
     dbg = {"bins": bins, "perm": perm, "plan": plan, "buffers": bufs}
     return pts, cols, nrm, total, status, dbg
 
@@ -431,6 +450,13 @@ def config_parser(argv=None):
         raise AttributeError("Cannot use masks when no transforms have been provided")
     if args.renderer_type != "cuda" and args.surface_distance_std is not None:
         raise AttributeError("Surface distance calculations only supported in CUDA renderer")
+    if args.clean_pointcloud or args.generate_mesh:
+        # Open3D post-processing is outside this build: fail before any loading / rendering
+        try:
+            import open3d  # noqa: F401
+        except ImportError:
+            raise AttributeError("--clean_pointcloud / --generate_mesh need Open3D, which is not installed")
+        raise AttributeError("--clean_pointcloud / --generate_mesh (Open3D post-processing) are not part of this build")
 
     return args
 

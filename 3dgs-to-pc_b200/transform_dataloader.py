@@ -53,6 +53,8 @@ def load_colmap_bin_data(input_path, skip_rate=0):
             name = b""
             while True:
                 c = f.read(1)
+                if c == b"":
+                    raise EOFError("images.bin is truncated (image name not NUL-terminated)")
                 if c == b"\x00":
                     break
                 name += c

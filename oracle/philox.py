@@ -1,7 +1,7 @@
 """Philox4x32-10 + Box-Muller, numpy restatement of the kernel's random stream (csrc/common.cuh).
 
 Stream definition: key = (seed_lo, seed_hi), counter = (gid, sample, attempt, call_id); the four 32-bit outputs
-give u1..u4 in (0,1) via ((x >> 8) + 0.5) * 2^-24, and
+give u1..u4 in (0,1) via ((x >> 9) + 0.5) * 2^-23 (exact in fp32), and
     eps = (sqrt(-2 ln u1) cos(2 pi u2), sqrt(-2 ln u1) sin(2 pi u2), sqrt(-2 ln u3) cos(2 pi u4)).
 This plays the role of torch's `_standard_normal` draw inside MultivariateNormal.rsample
 (torch/distributions/multivariate_normal.py:251-254; call site gauss_to_pc.py:149): eps[s, i, :] is the draw for
@@ -34,7 +34,7 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def _unit(x):
-    return ((x >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -24)
+    return ((x >> np.uint32(9)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -23)
 
 
 def draw_eps(gids, k, attempt, seed, call_id=0):
@@ -46,8 +46,8 @@ def draw_eps(gids, k, attempt, seed, call_id=0):
                                np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF))
     u1, u2, u3, u4 = _unit(x), _unit(y), _unit(z), _unit(w)
     two_pi = np.float32(6.283185307179586)
-    ra = np.sqrt(np.float32(-2.0) * np.log(u1))
-    rb = np.sqrt(np.float32(-2.0) * np.log(u3))
+    ra = np.sqrt(np.maximum(np.float32(0.0), np.float32(-2.0) * np.log(u1)))
+    rb = np.sqrt(np.maximum(np.float32(0.0), np.float32(-2.0) * np.log(u3)))
     e = np.empty((k, gids.shape[0], 3), dtype=np.float32)
     e[..., 0] = ra * np.cos(two_pi * u2)
     e[..., 1] = ra * np.sin(two_pi * u2)

@@ -82,7 +82,7 @@ def test_tables_reproduce_reference_order(n, P, exact, attempts):
     bin_of = lut[ppg.numpy()]
     order = np.argsort(bin_of, kind="stable")
     perm = order[: sum(c for (_, _, _, c) in bins)]
-    A = min(attempts, config.MAX_ATTEMPTS_STORED)
+    A = min(attempts, config.ATTEMPTS_STORED_FIRST)
     plan = sampler.SamplePlan([(k - 1, c) for (_, _, k, c) in bins], A)
     pts, cols, nr = emulate(plan, perm, sc["xyz"], cov, colours, nrm, np.arange(n), attempts, 2.0, eps_fn)
     assert pts.shape == o["points"].shape
