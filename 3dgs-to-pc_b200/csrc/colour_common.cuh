@@ -11,6 +11,16 @@
 #define NODE_SPLIT 2  // exists and was split into 4 children (gauss_render.py:319-335)
 #define NODE_LEAF 3   // exists and is rendered
 
+// node range of a Gaussian at the first leaf-candidate level, packed 8 bits per bound
+#define G2PC_RANGE_MAX_LEVEL 8
+#define G2PC_RANGE_EMPTY 0x00000001u  // xlo = 1 > xhi = 0
+__host__ __device__ __forceinline__ uint32_t g2pc_pack_range(int xlo, int xhi, int ylo, int yhi) {
+    return (uint32_t)xlo | ((uint32_t)xhi << 8) | ((uint32_t)ylo << 16) | ((uint32_t)yhi << 24);
+}
+__host__ __device__ __forceinline__ void g2pc_unpack_range(uint32_t r, int& xlo, int& xhi, int& ylo, int& yhi) {
+    xlo = (int)(r & 255u); xhi = (int)((r >> 8) & 255u); ylo = (int)((r >> 16) & 255u); yhi = (int)(r >> 24);
+}
+
 struct QtMeta {
     int32_t num_levels;  // tabulated levels 0..num_levels-1
     int32_t max_gaussians_per_tile;

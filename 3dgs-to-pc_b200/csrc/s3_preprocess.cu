@@ -7,18 +7,21 @@
 //   gauss_render.py:349      conic = inverse(cov2d)
 //   gauss_render.py:43-99    eval_sh (+0.5, clamp >= 0 as forward.cu:65-72) when SH coefficients are supplied
 //   gauss_render.py:301-319  tile membership: min(rect_max, tile_max) > max(rect_min, tile_min), strict, fp32
-// One thread per Gaussian, 2048 Gaussians per CTA.  Membership is evaluated by range queries on the per-level interval
-// tables (g2pc/quadtree.py) instead of testing every tile against every Gaussian; the per-node overlap counts are
-// accumulated in a shared-memory histogram and flushed once per CTA (a few thousand global atomics per CTA instead
-// of ~7 per Gaussian on ~1000 hot addresses).
+// One thread per Gaussian, 1024 Gaussians per CTA.  Inputs come from the packed geometry array built once per renderer
+// (g2pc_pack_geometry: 3 x float4 per Gaussian = xyz, Sigma as 6 floats, log2(opacity); three 16-byte loads per thread,
+// a warp reads 1536 contiguous bytes) and the SH rows (16-byte loads).  Membership is evaluated by range queries on the
+// per-level interval tables (g2pc/quadtree.py) instead of testing every tile against every Gaussian, and only on the
+// CANDIDATE levels (levels that have nodes small enough to be leaves): a node that is larger than max_tile_size splits
+// whatever its count, so its count is never needed.  The per-node overlap counts are accumulated in a shared-memory
+// histogram and flushed once per CTA.  The node range at the first candidate level is packed into the high word of
+// `val` (low word = Gaussian id): after the depth sort the multisplit kernels (s4_tree.cu) read their ranges from the
+// sorted stream and never gather.
 #include "colour_common.cuh"
 
 namespace {
 
 struct PreParams {
-    const float* xyz;
-    const float* cov;
-    const float* opacity;
+    const float4* geom;    // 3 x float4 per Gaussian: {x,y,z,S00} {S01,S02,S11,S12} {S22,log2(opacity),0,0}
     const float* colours;  // (n,3) f32 or null
     const float* shs;      // (n,3,sh_stride) f32 or null
     int32_t sh_stride, sh_degree;
@@ -30,8 +33,11 @@ struct PreParams {
     float4* proj;
     uint32_t* node_cnt;
     uint32_t* depth_key;  // bits(-z_view) for Gaussians in front of the camera, 0xFFFFFFFF otherwise
-    uint32_t* touched;    // number of leaf-candidate nodes the Gaussian overlaps (upper bound of its instances)
+    unsigned long long* val;  // (packed node range at the base level << 32) | Gaussian id
     int32_t nodes_2d;     // histogram entries (0: no shared-memory histogram, global atomics)
+    int32_t hist_off;     // first 2-D node of the shared-memory histogram (= off2(base level))
+    uint32_t level_mask;  // bit l: level l has leaf-candidate nodes
+    int32_t base_level;   // lowest set bit of level_mask
 };
 
 constexpr int PRE_PER_CTA = 1024;
@@ -98,7 +104,8 @@ __global__ void __launch_bounds__(256, 4) preprocess_kernel(const PreParams p) {
 
     const float* V = p.cam.view;
     const float* P = p.cam.proj;
-    const float m0 = p.xyz[3 * i], m1 = p.xyz[3 * i + 1], m2 = p.xyz[3 * i + 2];
+    const float4 g0 = __ldg(p.geom + 3 * i), g1 = __ldg(p.geom + 3 * i + 1), g2 = __ldg(p.geom + 3 * i + 2);
+    const float m0 = g0.x, m1 = g0.y, m2 = g0.z;
 
     // p_view = [mu, 1] @ V   (row-vector convention)
     float pv[4];
@@ -107,7 +114,7 @@ __global__ void __launch_bounds__(256, 4) preprocess_kernel(const PreParams p) {
     const bool in_front = pv[2] <= -0.000001f;
 
     float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0;
-    uint32_t n_touched = 0;
+    uint32_t range = G2PC_RANGE_EMPTY;
     if (in_front) {
         // p_h = p_view @ P ; ndc = p_h / (w + 1e-6) ; pixel centre convention of gauss_render.py:435-436
         float ph[4];
@@ -135,9 +142,8 @@ __global__ void __launch_bounds__(256, 4) preprocess_kernel(const PreParams p) {
             M[0][c] = fmaf(jb, V[4 * c + 2], ja * V[4 * c + 0]);
             M[1][c] = fmaf(jd, V[4 * c + 2], jc * V[4 * c + 1]);
         }
-        float S[9];
-#pragma unroll
-        for (int c = 0; c < 9; ++c) S[c] = p.cov[9 * i + c];
+        // Sigma is symmetric by construction (S1 kernel); the packed copy keeps the upper triangle
+        const float S[9] = {g0.w, g1.x, g1.y, g1.x, g1.z, g1.w, g1.y, g1.w, g2.x};
         float A[2][3], B[2][3];
 #pragma unroll
         for (int r = 0; r < 2; ++r)
@@ -174,35 +180,31 @@ __global__ void __launch_bounds__(256, 4) preprocess_kernel(const PreParams p) {
         }
         q0 = make_float4(mx, my, k00 * K, (k01 + k10) * K);
         // alpha = min(0.99, opacity * exp(power)) = min(0.99, exp2(power' + log2(opacity)))
-        q1 = make_float4(k11 * K, log2f(p.opacity[i]), rgb.x, rgb.y);
+        q1 = make_float4(k11 * K, g2.y, rgb.x, rgb.y);
         q2 = make_float4(rgb.z, pv[2], radius, 1.0f);
 
         // ---- quadtree membership: flags for nodes that split anyway, exact counts for leaf candidates ----
         float x0, x1, y0, y1;
         gaussian_rect(mx, my, radius, p.cam.width, p.cam.height, x0, x1, y0, y1);
         const float isx0 = 1.0f / (float)p.cam.width, isy0 = 1.0f / (float)p.cam.height;
-        for (int l = 0; l < p.meta.num_levels; ++l) {
+        for (int l = p.base_level; l < p.meta.num_levels; ++l) {
+            if (!((p.level_mask >> l) & 1u)) continue;  // every node of this level splits by its size: counts unused
             const int o1 = (1 << l) - 1;
             int xlo, xhi, ylo, yhi;
             axis_range(T.xs + o1, T.xe + o1, l, x0, x1, isx0 * (float)(1 << l), xlo, xhi);
             if (xlo > xhi) continue;
             axis_range(T.ys + o1, T.ye + o1, l, y0, y1, isy0 * (float)(1 << l), ylo, yhi);
             if (ylo > yhi) continue;
+            if (l == p.base_level) range = g2pc_pack_range(xlo, xhi, ylo, yhi);
             uint32_t* cnt = p.node_cnt + off2(l);
             for (int iy = ylo; iy <= yhi; ++iy) {
                 if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy)) continue;
                 const int fy = T.yf[o1 + iy];
                 for (int ix = xlo; ix <= xhi; ++ix) {
                     if (!axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) continue;
-                    const bool big = ((fy | T.xf[o1 + ix]) & QT_FLAG_BIG) != 0;
-                    n_touched += big ? 0u : 1u;
-                    if (use_hist) {
-                        atomicAdd(s_hist + off2(l) + (iy << l) + ix, 1u);
-                    } else {
-                        uint32_t* c = cnt + (iy << l) + ix;
-                        if (big) { if (*(volatile uint32_t*)c == 0u) *c = 1u; }  // non-empty flag
-                        else atomicAdd(c, 1u);
-                    }
+                    if ((fy | T.xf[o1 + ix]) & QT_FLAG_BIG) continue;  // splits whatever its count
+                    if (use_hist) atomicAdd(s_hist + (off2(l) - p.hist_off) + (iy << l) + ix, 1u);
+                    else atomicAdd(cnt + (iy << l) + ix, 1u);
                 }
             }
         }
@@ -210,75 +212,28 @@ __global__ void __launch_bounds__(256, 4) preprocess_kernel(const PreParams p) {
     float4* rec = p.proj + 3 * i;
     rec[0] = q0; rec[1] = q1; rec[2] = q2;
     p.depth_key[i] = in_front ? __float_as_uint(-pv[2]) : 0xFFFFFFFFu;
-    p.touched[i] = n_touched;
+    p.val[i] = ((unsigned long long)range << 32) | (unsigned long long)(uint32_t)i;
   }
     if (use_hist) {
         __syncthreads();
         for (int k = threadIdx.x; k < p.nodes_2d; k += blockDim.x) {
             const uint32_t v = s_hist[k];
-            if (v) atomicAdd(p.node_cnt + k, v);
+            if (v) atomicAdd(p.node_cnt + p.hist_off + k, v);
         }
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// S4b.  Gaussians are visited in depth order (order[k] = k-th nearest); Gaussian order[k] writes one (leaf id, gid)
-// pair per leaf-candidate node it overlaps at offs[k].. — the leaf id is 0xFFFFFFFF when the node is not a leaf, so
-// the following stable radix sort on the leaf id leaves every leaf's list depth-ordered and the padding at the end.
-struct EmitParams {
-    const float4* proj;
-    const uint32_t* order;
-    const uint32_t* incl;     // inclusive scan of touched[order[k]]
-    const uint32_t* touched;
-    int64_t n;
-    int32_t width, height;
-    QtMeta meta;
-    QtTables tab;
-    int32_t n1;
-    const uint8_t* node_state;
-    const int32_t* leaf_of_node;
-    uint32_t* inst_leaf;
-    uint32_t* inst_gid;
-    uint32_t level_mask;  // bit l set: level l has nodes that are not forced to split (leaf candidates)
-};
-
-__global__ void __launch_bounds__(256) emit_instances_kernel(const EmitParams p) {
-    extern __shared__ int32_t smem_tab[];
-    const QtTables T = load_tables(p.tab, p.n1, smem_tab);
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= p.n) return;
-    const uint32_t g = p.order[k];
-    const uint32_t nt = p.touched[g];
-    if (nt == 0u) return;
-    int64_t pos = (int64_t)p.incl[k] - nt;
-    const float4 q2 = p.proj[3 * (int64_t)g + 2];
-    const float4 q0 = p.proj[3 * (int64_t)g];
-    float x0, x1, y0, y1;
-    gaussian_rect(q0.x, q0.y, q2.z, p.width, p.height, x0, x1, y0, y1);
-    const float isx0 = 1.0f / (float)p.width, isy0 = 1.0f / (float)p.height;
-    for (int l = 0; l < p.meta.num_levels; ++l) {
-        if (!((p.level_mask >> l) & 1)) continue;  // no leaf-candidate node at this level
-        const int o1 = (1 << l) - 1;
-        int xlo, xhi, ylo, yhi;
-        axis_range(T.xs + o1, T.xe + o1, l, x0, x1, isx0 * (float)(1 << l), xlo, xhi);
-        if (xlo > xhi) continue;
-        axis_range(T.ys + o1, T.ye + o1, l, y0, y1, isy0 * (float)(1 << l), ylo, yhi);
-        if (ylo > yhi) continue;
-        const int o2 = off2(l);
-        for (int iy = ylo; iy <= yhi; ++iy) {
-            if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy)) continue;
-            const int fy = T.yf[o1 + iy];
-            for (int ix = xlo; ix <= xhi; ++ix) {
-                if (!axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) continue;
-                if ((fy | T.xf[o1 + ix]) & QT_FLAG_BIG) continue;  // not counted in touched[]
-                const int node = o2 + (iy << l) + ix;
-                const uint32_t leaf = (p.node_state[node] == NODE_LEAF) ? (uint32_t)p.leaf_of_node[node] : 0xFFFFFFFFu;
-                p.inst_leaf[pos] = leaf;
-                p.inst_gid[pos] = g;
-                ++pos;
-            }
-        }
-    }
+// Packed geometry (once per renderer): xyz (n,3), Sigma (n,3,3) and opacity (n) -> 3 float4 per Gaussian, log2 of the
+// opacity taken here (the blend evaluates alpha = min(0.99, exp2(power' + log2 o))).
+__global__ void __launch_bounds__(256) pack_geometry_kernel(const float* __restrict__ xyz, const float* __restrict__ cov,
+                                                            const float* __restrict__ opacity, int64_t n,
+                                                            float4* __restrict__ geom) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* c = cov + 9 * i;
+    geom[3 * i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], c[0]);
+    geom[3 * i + 1] = make_float4(c[1], c[2], c[4], c[5]);
+    geom[3 * i + 2] = make_float4(c[8], log2f(opacity[i]), 0.0f, 0.0f);
 }
 
 QtTables make_tables(const int32_t* tables, int n1) {
@@ -290,59 +245,50 @@ QtTables make_tables(const int32_t* tables, int n1) {
 
 }  // namespace
 
-extern "C" int g2pc_preprocess(const float* xyz, const float* cov, const float* opacity, const float* colours,
-                               const float* shs, int32_t sh_stride, int32_t sh_degree, int64_t n,
-                               const g2pc_camera_t* cam_host, const int32_t* tables, int32_t num_levels,
-                               int32_t max_gaussians_per_tile, void* proj, uint32_t* node_cnt, uint32_t* depth_key,
-                               uint32_t* touched, void* stream) {
+extern "C" int g2pc_pack_geometry(const float* xyz, const float* cov, const float* opacity, int64_t n, void* geom,
+                                  void* stream) {
     G2PC_CHECK_ARG(n >= 0, "n < 0");
     if (n == 0) return G2PC_OK;
-    G2PC_CHECK_ARG(xyz && cov && opacity && cam_host && tables && proj && node_cnt && depth_key && touched,
-                   "null pointer");
-    G2PC_CHECK_ARG((colours != nullptr) != (shs != nullptr), "provide exactly one of colours / shs");
-    G2PC_CHECK_ARG(num_levels >= 1 && num_levels <= G2PC_MAX_LEVELS, "bad num_levels");
-    G2PC_CHECK_ARG(!shs || (sh_degree >= 0 && sh_degree <= 3 && sh_stride >= (sh_degree + 1) * (sh_degree + 1)),
-                   "SH degree must be 0..3 and sh_stride >= (deg+1)^2");
-    PreParams p;
-    p.xyz = xyz; p.cov = cov; p.opacity = opacity; p.colours = colours; p.shs = shs;
-    p.sh_stride = sh_stride; p.sh_degree = sh_degree; p.n = n; p.cam = *cam_host;
-    p.meta.num_levels = num_levels; p.meta.max_gaussians_per_tile = max_gaussians_per_tile;
-    p.meta.width = cam_host->width; p.meta.height = cam_host->height;
-    p.n1 = (1 << num_levels) - 1;
-    p.tab = make_tables(tables, p.n1);
-    p.proj = (float4*)proj; p.node_cnt = node_cnt; p.depth_key = depth_key; p.touched = touched;
-    const int nodes_2d = ((1 << (2 * num_levels)) - 1) / 3;
-    p.nodes_2d = nodes_2d <= 24 * 1024 ? nodes_2d : 0;  // histogram in shared memory when it fits (<= 96 KB)
-    const size_t smem = (size_t)6 * p.n1 * sizeof(int32_t) + (size_t)p.nodes_2d * sizeof(uint32_t);
-    if (smem > 48 * 1024)
-        G2PC_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    preprocess_kernel<<<(unsigned)((n + PRE_PER_CTA - 1) / PRE_PER_CTA), 256, smem, (cudaStream_t)stream>>>(p);
+    G2PC_CHECK_ARG(xyz && cov && opacity && geom, "null pointer");
+    G2PC_CHECK_ARG(((uintptr_t)geom & 15) == 0, "geom must be 16-byte aligned");
+    pack_geometry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(xyz, cov, opacity, n,
+                                                                                         (float4*)geom);
     G2PC_CHECK_LAUNCH();
     return G2PC_OK;
 }
 
-extern "C" int g2pc_emit_instances(const void* proj, const uint32_t* order, const uint32_t* incl,
-                                   const uint32_t* touched, int64_t n, int32_t width, int32_t height,
-                                   const int32_t* tables, int32_t num_levels, uint32_t level_mask,
-                                   const uint8_t* node_state, const int32_t* leaf_of_node, uint32_t* inst_leaf,
-                                   uint32_t* inst_gid, void* stream) {
+extern "C" int g2pc_preprocess(const void* geom, const float* colours, const float* shs, int32_t sh_stride,
+                               int32_t sh_degree, int64_t n, const g2pc_camera_t* cam_host, const int32_t* tables,
+                               int32_t num_levels, uint32_t level_mask, void* proj, uint32_t* node_cnt,
+                               uint32_t* depth_key, uint64_t* val, void* stream) {
     G2PC_CHECK_ARG(n >= 0, "n < 0");
     if (n == 0) return G2PC_OK;
-    G2PC_CHECK_ARG(proj && order && incl && touched && tables && node_state && leaf_of_node && inst_leaf && inst_gid,
-                   "null pointer");
+    G2PC_CHECK_ARG(geom && cam_host && tables && proj && node_cnt && depth_key && val, "null pointer");
+    G2PC_CHECK_ARG(n <= 0xFFFFFFFFll, "more than 2^32 Gaussians");
+    G2PC_CHECK_ARG((colours != nullptr) != (shs != nullptr), "provide exactly one of colours / shs");
     G2PC_CHECK_ARG(num_levels >= 1 && num_levels <= G2PC_MAX_LEVELS, "bad num_levels");
-    EmitParams p;
-    p.proj = (const float4*)proj; p.order = order; p.incl = incl; p.touched = touched; p.n = n;
-    p.width = width; p.height = height;
-    p.meta.num_levels = num_levels; p.meta.max_gaussians_per_tile = 0; p.meta.width = width; p.meta.height = height;
+    G2PC_CHECK_ARG(!shs || (sh_degree >= 0 && sh_degree <= 3 && sh_stride >= (sh_degree + 1) * (sh_degree + 1)),
+                   "SH degree must be 0..3 and sh_stride >= (deg+1)^2");
+    G2PC_CHECK_ARG(level_mask != 0u && (level_mask >> num_levels) == 0u, "level_mask must name tabulated levels");
+    PreParams p;
+    p.geom = (const float4*)geom; p.colours = colours; p.shs = shs;
+    p.sh_stride = sh_stride; p.sh_degree = sh_degree; p.n = n; p.cam = *cam_host;
+    p.meta.num_levels = num_levels; p.meta.max_gaussians_per_tile = 0;
+    p.meta.width = cam_host->width; p.meta.height = cam_host->height;
     p.n1 = (1 << num_levels) - 1;
     p.tab = make_tables(tables, p.n1);
-    p.node_state = node_state; p.leaf_of_node = leaf_of_node; p.inst_leaf = inst_leaf; p.inst_gid = inst_gid;
+    p.proj = (float4*)proj; p.node_cnt = node_cnt; p.depth_key = depth_key; p.val = (unsigned long long*)val;
     p.level_mask = level_mask;
-    const size_t smem = (size_t)6 * p.n1 * sizeof(int32_t);
+    p.base_level = __builtin_ctz(level_mask);
+    G2PC_CHECK_ARG(p.base_level <= G2PC_RANGE_MAX_LEVEL, "first leaf-candidate level too deep for the packed node range");
+    const int nodes_all = ((1 << (2 * num_levels)) - 1) / 3;
+    p.hist_off = ((1 << (2 * p.base_level)) - 1) / 3;
+    const int nodes_hist = nodes_all - p.hist_off;       // candidate levels only
+    p.nodes_2d = nodes_hist <= 24 * 1024 ? nodes_hist : 0;  // histogram in shared memory when it fits (<= 96 KB)
+    const size_t smem = (size_t)6 * p.n1 * sizeof(int32_t) + (size_t)p.nodes_2d * sizeof(uint32_t);
     if (smem > 48 * 1024)
-        G2PC_CUDA(cudaFuncSetAttribute(emit_instances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    emit_instances_kernel<<<(unsigned)((n + 255) / 256), 256, smem, (cudaStream_t)stream>>>(p);
+        G2PC_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    preprocess_kernel<<<(unsigned)((n + PRE_PER_CTA - 1) / PRE_PER_CTA), 256, smem, (cudaStream_t)stream>>>(p);
     G2PC_CHECK_LAUNCH();
     return G2PC_OK;
 }

@@ -1,40 +1,52 @@
-// s4_tree.cu — S4: resolve the python renderer's tile quadtree on the device, then depth-sort every leaf's list.
+// s4_tree.cu — S4: resolve the python renderer's tile quadtree on the device, then build every leaf's depth-ordered list.
 //
 // Reference semantics restated (not copied): gauss_render.py:290-344
 //   BFS over tiles; a tile is skipped if w <= 1 or h <= 1 (:301), background-filled if no Gaussian overlaps it
 //   (:313-315), split into TL, BL, TR, BR children if it holds more than max_gaussians_per_tile Gaussians or is wider /
 //   taller than max_tile_size (:319-335), else rendered with its Gaussians ordered nearest-first (:340-344).
-// The per-node overlap counts come from the preprocess kernel; one CTA walks the levels top-down (a level has at most
-// a few thousand nodes), numbers the leaves in the reference's BFS order (level-major, then child-rank path order) and
-// lays out the instance / pixel offsets.
+// Role of rasterizer_impl.cu:69-137,285-326 (duplicateWithKeys + 64-bit radix sort + identifyTileRanges) in the CUDA
+// back-end of the reference; none of its structure is kept.
 //
-// Depth ordering without a per-leaf sort: the Gaussians are sorted ONCE per camera by view depth (N keys), instances
-// are emitted in that order, and a stable LSD radix sort on the leaf id alone (ceil(log2(#leaves)) bits, 2 passes)
-// groups them by leaf while keeping the depth order inside every leaf.  The radix sorts / scan are library calls
-// (cub::DeviceRadixSort, cub::DeviceScan).
+// Pipeline per camera (all sizes stay on the device; the host never waits for a count):
+//   1. g2pc_depth_sort      one radix sort of N (depth key, value) pairs, value = (packed node range << 32 | Gaussian id)
+//                           written by the preprocess kernel (cub::DeviceRadixSort, library call).
+//   2. g2pc_build_tree      one CTA walks the levels top-down on the per-node overlap counts of the preprocess kernel,
+//                           numbers the leaves in the reference's BFS order (level-major, then child-rank path order),
+//                           lays out instance / pixel offsets, sorts the leaves heaviest-first for the blend and writes
+//                           the frame header.  A frame that does not fit the caller's buffers (or needs a deeper table)
+//                           sets the sticky POISON word: every later kernel of this and the following frames becomes a
+//                           no-op until the host has read the header, fixed the sizes and replayed.
+//   3. g2pc_multisplit      stable one-pass-per-chunk multisplit of the depth-ordered stream into the leaves' lists:
+//        count    CTA c takes 256 consecutive sorted entries and counts its instances per leaf (shared-memory histogram)
+//        scan     per leaf, exclusive prefix over the chunks (+ the leaf's list offset)          -> matrix[c][leaf]
+//        scatter  CTA c marks bit (leaf, k) for every instance in a shared-memory bit matrix (order-free atomicOr), then
+//                 one thread per leaf walks its 256 bits in order and appends the Gaussian ids at matrix[c][leaf]:
+//                 the lists come out depth-ordered without any sort of the ~7 N instances (the round-1 path emitted
+//                 (leaf, id) pairs and ran a 2-pass 20 M-pair radix sort per camera).
 #include <cub/cub.cuh>
-#include <thrust/iterator/counting_iterator.h>
-#include <thrust/iterator/transform_iterator.h>
 #include "colour_common.cuh"
 
 namespace {
 
 constexpr int TB = 1024;
+constexpr int SORT_CAP = 4096;  // leaves sorted heaviest-first in shared memory (more leaves: launch order = BFS order)
 
 struct TreeParams {
     QtMeta meta;
     QtTables tab;
     int32_t n1;
-    const uint32_t* node_cnt;
+    uint32_t* node_cnt;      // read, then cleared for the next frame
     uint8_t* node_state;
-    int32_t* leaf_of_node;
+    int32_t* node_leaf;      // per node: leaf id, -1 (no leaf: empty / absent / dropped) or -2 (split)
     g2pc_leaf_t* leaves;
-    int32_t* seg_begin;  // max_leaves + 1
-    int32_t* leaf_order; // leaves sorted by descending work (longest-processing-time-first launch order)
+    int32_t* leaf_order;     // leaves sorted by descending work (longest-processing-time-first launch order)
     int32_t max_leaves;
-    const uint32_t* incl;  // inclusive scan of touched[] in depth order (last entry = instance upper bound) or null
-    int64_t n;
-    int32_t* header;  // G2PC_HDR_WORDS
+    int64_t inst_capacity, pix_capacity, matrix_capacity;
+    int32_t ms_chunks;
+    int32_t frame;
+    int32_t* header;         // G2PC_HDR_WORDS
+    int32_t* work_counters;  // G2PC_WORK_COUNTERS ints, cleared here for the blend of this frame
+    int32_t nodes_2d;
 };
 
 __device__ __forceinline__ int off2d(int l) { return ((1 << (2 * l)) - 1) / 3; }
@@ -80,10 +92,13 @@ __device__ __forceinline__ void deinterleave(int key, int level, int& ix, int& i
 __global__ void __launch_bounds__(TB) tree_kernel(const TreeParams p) {
     __shared__ int s_warp[33];
     __shared__ int s_flags[2];
+    __shared__ unsigned long long s_sort[SORT_CAP];
+    if (p.header[G2PC_HDR_POISON] != 0) return;  // an earlier frame failed: keep its header for the host
     const int L = p.meta.num_levels;
     if (threadIdx.x == 0) { s_flags[0] = 0; s_flags[1] = 0; }
     __syncthreads();
     int leaf_base = 0;
+    long long inst_total = 0;
     for (int l = 0; l < L; ++l) {
         const int nn = 1 << (2 * l);
         const int o1 = (1 << l) - 1, o2 = off2d(l);
@@ -100,14 +115,19 @@ __global__ void __launch_bounds__(TB) tree_kernel(const TreeParams p) {
                     exists = p.node_state[pnode] == NODE_SPLIT;
                 }
                 uint8_t st = NODE_NONE;
+                int32_t nl = -1;
                 if (exists) {
                     const int fx = p.tab.xf[o1 + ix], fy = p.tab.yf[o1 + iy];
                     if (!((fx | fy) & QT_FLAG_DROPPED)) {
                         cnt = p.node_cnt[node];
-                        if (cnt == 0) st = NODE_EMPTY;
-                        else if (((fx | fy) & QT_FLAG_BIG) || cnt > (uint32_t)p.meta.max_gaussians_per_tile) {
+                        // a node larger than max_tile_size splits whatever it holds (its count is not even collected):
+                        // if it is empty so are its descendants, and the same leaves come out (gauss_render.py:313-335)
+                        const bool big = ((fx | fy) & QT_FLAG_BIG) != 0;
+                        if (!big && cnt == 0) st = NODE_EMPTY;
+                        else if (big || cnt > (uint32_t)p.meta.max_gaussians_per_tile) {
                             st = NODE_SPLIT;
-                            if (l == L - 1) { st = NODE_NONE; s_flags[0] = 1; }  // deeper than the tabulated levels
+                            nl = -2;
+                            if (l == L - 1) { st = NODE_NONE; nl = -1; s_flags[0] = 1; }  // deeper than the tabulated levels
                         } else {
                             st = NODE_LEAF;
                             is_leaf = 1;
@@ -115,6 +135,7 @@ __global__ void __launch_bounds__(TB) tree_kernel(const TreeParams p) {
                     }
                 }
                 p.node_state[node] = st;
+                p.node_leaf[node] = nl;
             }
             int tot;
             const int pre = block_scan_1024(is_leaf, s_warp, tot);
@@ -131,7 +152,7 @@ __global__ void __launch_bounds__(TB) tree_kernel(const TreeParams p) {
                     lf.pix_offset = 0;
                     lf.node = node;
                     p.leaves[li] = lf;
-                    p.leaf_of_node[node] = li;
+                    p.node_leaf[node] = li;
                 } else {
                     s_flags[1] = 1;
                 }
@@ -142,136 +163,347 @@ __global__ void __launch_bounds__(TB) tree_kernel(const TreeParams p) {
     }
     const int nl = leaf_base < p.max_leaves ? leaf_base : p.max_leaves;
     // exclusive scans of the instance counts and pixel counts over the leaves, in order
-    int inst_base = 0, pix_base = 0;
+    int pix_base = 0;
     for (int k0 = 0; k0 < nl; k0 += TB) {
         const int i = k0 + threadIdx.x;
         int c = 0, a = 0;
-        if (i < nl) { c = p.leaves[i].inst_count; a = p.leaves[i].w * p.leaves[i].h; }
+        // every list starts on a 16-byte boundary (the blend stages id chunks with TMA bulk copies): pad to 4 ids
+        if (i < nl) { c = (p.leaves[i].inst_count + 3) & ~3; a = p.leaves[i].w * p.leaves[i].h; }
         int tc, ta;
         const int pc = block_scan_1024(c, s_warp, tc);
         const int pa = block_scan_1024(a, s_warp, ta);
         if (i < nl) {
-            p.leaves[i].inst_begin = inst_base + pc;
+            // 32-bit list offsets: a frame with more than 2^31 instances is reported through the capacity check below
+            p.leaves[i].inst_begin = (int32_t)(inst_total + pc);
             p.leaves[i].pix_offset = pix_base + pa;
-            p.seg_begin[i] = inst_base + pc;
         }
-        inst_base += tc;
+        inst_total += tc;
         pix_base += ta;
     }
     __syncthreads();
-    // launch order for the blend: heaviest leaves first (rank by instances x pixels, ties by index)
-    for (int i = threadIdx.x; i < nl; i += TB) {
-        const long long wi = (long long)p.leaves[i].inst_count * (p.leaves[i].w * p.leaves[i].h);
-        int rank = 0;
-        for (int j = 0; j < nl; ++j) {
-            const long long wj = (long long)p.leaves[j].inst_count * (p.leaves[j].w * p.leaves[j].h);
-            rank += (wj > wi || (wj == wi && j < i)) ? 1 : 0;
+    // launch order for the blend: heaviest leaves first (instances x pixels, ties by index) — bitonic sort in smem
+    if (nl <= SORT_CAP) {
+        int m = 1;
+        while (m < nl) m <<= 1;
+        for (int i = threadIdx.x; i < m; i += TB) {
+            unsigned long long key = ~0ull;
+            if (i < nl) {
+                unsigned long long w = (unsigned long long)p.leaves[i].inst_count *
+                                       (unsigned long long)(p.leaves[i].w * p.leaves[i].h);
+                w = w < (1ull << 44) - 1ull ? w : (1ull << 44) - 1ull;
+                key = (((1ull << 44) - 1ull - w) << 16) | (unsigned long long)i;  // ascending key = descending work
+            }
+            s_sort[i] = key;
         }
-        p.leaf_order[rank] = i;
+        __syncthreads();
+        for (int k = 2; k <= m; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < m; i += TB) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const unsigned long long a = s_sort[i], b = s_sort[ixj];
+                        const bool up = (i & k) == 0;
+                        if ((a > b) == up) { s_sort[i] = b; s_sort[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (int i = threadIdx.x; i < nl; i += TB) p.leaf_order[i] = (int)(s_sort[i] & 0xFFFFull);
+    } else {
+        for (int i = threadIdx.x; i < nl; i += TB) p.leaf_order[i] = i;
     }
+    // the counts are consumed: clear them for the next frame's preprocess
+    for (int k = threadIdx.x; k < p.nodes_2d; k += TB) p.node_cnt[k] = 0u;
+    if (threadIdx.x < G2PC_WORK_COUNTERS) p.work_counters[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
-        p.header[G2PC_HDR_TOTAL_UPPER] = (p.incl && p.n > 0) ? (int32_t)p.incl[p.n - 1] : 0;
-        p.seg_begin[nl] = inst_base;
+        const int cap_over = (inst_total > p.inst_capacity || (long long)pix_base > p.pix_capacity ||
+                              (long long)p.ms_chunks * (long long)nl > p.matrix_capacity || inst_total > 0x7FFFFFFFll)
+                                 ? 1 : 0;
         p.header[G2PC_HDR_NUM_LEAVES] = leaf_base;
-        p.header[G2PC_HDR_TOTAL_INST] = inst_base;
+        p.header[G2PC_HDR_TOTAL_INST] = (int32_t)(inst_total & 0xFFFFFFFFll);
+        p.header[G2PC_HDR_TOTAL_INST_HI] = (int32_t)(inst_total >> 32);
         p.header[G2PC_HDR_TOTAL_PIX] = pix_base;
         p.header[G2PC_HDR_NEED_DEEPER] = s_flags[0];
         p.header[G2PC_HDR_LEAF_OVERFLOW] = s_flags[1];
+        p.header[G2PC_HDR_CAP_OVERFLOW] = cap_over;
+        p.header[G2PC_HDR_FRAME] = p.frame;
+        if (s_flags[0] | s_flags[1] | cap_over) p.header[G2PC_HDR_POISON] = p.frame + 1;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Multisplit.  An entry of the sorted stream is (range << 32 | gid); its leaves are enumerated from the packed node range
+// at the base level; Gaussians that touch a split node re-derive their rect from the projection record and query the
+// deeper candidate levels (count-driven splits only — rare).
+struct MsParams {
+    const unsigned long long* val_sorted;
+    int64_t n;
+    const float4* proj;
+    int32_t width, height;
+    QtMeta meta;
+    QtTables tab;
+    int32_t n1;
+    uint32_t level_mask;
+    int32_t base_level;
+    const int32_t* node_leaf;
+    const int32_t* header;
+    const g2pc_leaf_t* leaves;
+    uint32_t* matrix;      // [chunk][num_leaves]: counts, then absolute list offsets (in place)
+    uint32_t* inst_gid;
+    int32_t leaf_cap;      // leaves the shared-memory tables are sized for (<= max_leaves of the tree)
+};
+
+template <typename F>
+__device__ __forceinline__ void for_each_leaf(const MsParams& p, const QtTables& T, const int32_t* __restrict__ s_leaf,
+                                              uint32_t range, uint32_t gid, F f) {
+    int xlo, xhi, ylo, yhi;
+    g2pc_unpack_range(range, xlo, xhi, ylo, yhi);
+    if (xlo > xhi) return;
+    const int lb = p.base_level;
+    const int o1 = (1 << lb) - 1;
+    bool deeper = false;
+    for (int iy = ylo; iy <= yhi; ++iy) {
+        if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy)) continue;
+        for (int ix = xlo; ix <= xhi; ++ix) {
+            if (!axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) continue;
+            const int32_t v = s_leaf[(iy << lb) + ix];
+            if (v >= 0) f(v);
+            else if (v == -2) deeper = true;
+        }
+    }
+    if (!deeper || p.meta.num_levels <= lb + 1) return;
+    const float4 q0 = __ldg(p.proj + 3 * (int64_t)gid);
+    const float4 q2 = __ldg(p.proj + 3 * (int64_t)gid + 2);
+    float x0, x1, y0, y1;
+    gaussian_rect(q0.x, q0.y, q2.z, p.width, p.height, x0, x1, y0, y1);
+    const float isx0 = 1.0f / (float)p.width, isy0 = 1.0f / (float)p.height;
+    for (int l = lb + 1; l < p.meta.num_levels; ++l) {
+        if (!((p.level_mask >> l) & 1u)) continue;
+        const int ol = (1 << l) - 1;
+        int axlo, axhi, aylo, ayhi;
+        axis_range(T.xs + ol, T.xe + ol, l, x0, x1, isx0 * (float)(1 << l), axlo, axhi);
+        if (axlo > axhi) continue;
+        axis_range(T.ys + ol, T.ye + ol, l, y0, y1, isy0 * (float)(1 << l), aylo, ayhi);
+        if (aylo > ayhi) continue;
+        const int32_t* nl = p.node_leaf + off2d(l);
+        for (int iy = aylo; iy <= ayhi; ++iy) {
+            if (!axis_member(T.ys + ol, T.ye + ol, T.yf + ol, iy)) continue;
+            for (int ix = axlo; ix <= axhi; ++ix) {
+                if (!axis_member(T.xs + ol, T.xe + ol, T.xf + ol, ix)) continue;
+                const int32_t v = __ldg(nl + (iy << l) + ix);
+                if (v >= 0) f(v);
+            }
+        }
+    }
+}
+
+// shared memory of the count / scatter kernels: [6 * n1 table ints][4^base node->leaf ints][payload]
+__device__ __forceinline__ int32_t* ms_load_common(const MsParams& p, int32_t* smem, QtTables& T) {
+    T = load_tables(p.tab, p.n1, smem);  // ends with __syncthreads()
+    int32_t* s_leaf = smem + 6 * p.n1;
+    const int nb = 1 << (2 * p.base_level);
+    const int32_t* src = p.node_leaf + off2d(p.base_level);
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) s_leaf[i] = src[i];
+    return s_leaf;
+}
+
+template <int C>
+__global__ void __launch_bounds__(C) ms_count_kernel(const MsParams p) {
+    extern __shared__ int32_t smem_ms[];
+    if (p.header[G2PC_HDR_POISON] != 0) return;
+    const int nl = p.header[G2PC_HDR_NUM_LEAVES];
+    QtTables T;
+    int32_t* s_leaf = ms_load_common(p, smem_ms, T);
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_leaf + (1 << (2 * p.base_level)));
+    for (int i = threadIdx.x; i < nl; i += C) s_hist[i] = 0u;
+    __syncthreads();
+    const int64_t k = (int64_t)blockIdx.x * C + threadIdx.x;
+    if (k < p.n) {
+        const unsigned long long v = p.val_sorted[k];
+        for_each_leaf(p, T, s_leaf, (uint32_t)(v >> 32), (uint32_t)v, [&](int leaf) { atomicAdd(s_hist + leaf, 1u); });
+    }
+    __syncthreads();
+    uint32_t* row = p.matrix + (int64_t)blockIdx.x * nl;
+    for (int i = threadIdx.x; i < nl; i += C) row[i] = s_hist[i];
+}
+
+// per leaf (column): counts -> absolute offsets of the chunk's instances inside inst_gid.  CTA = 32 leaves x 32 row
+// segments; the matrix is read twice (sum, then rewrite).
+__global__ void __launch_bounds__(1024) ms_scan_kernel(const MsParams p, int32_t chunks) {
+    __shared__ uint32_t s_sum[32][33];
+    if (p.header[G2PC_HDR_POISON] != 0) return;
+    const int nl = p.header[G2PC_HDR_NUM_LEAVES];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int seg = (chunks + 31) / 32;
+    for (int leaf0 = blockIdx.x * 32; leaf0 < nl; leaf0 += gridDim.x * 32) {
+        const int leaf = leaf0 + tx;
+        const int r0 = ty * seg, r1 = min(chunks, r0 + seg);
+        uint32_t sum = 0;
+        if (leaf < nl)
+            for (int r = r0; r < r1; ++r) sum += p.matrix[(int64_t)r * nl + leaf];
+        s_sum[ty][tx] = sum;
+        __syncthreads();
+        if (ty == 0) {
+            uint32_t run = (leaf < nl) ? (uint32_t)p.leaves[leaf].inst_begin : 0u;
+            for (int s = 0; s < 32; ++s) { const uint32_t t = s_sum[s][tx]; s_sum[s][tx] = run; run += t; }
+        }
+        __syncthreads();
+        if (leaf < nl) {
+            uint32_t run = s_sum[ty][tx];
+            for (int r = r0; r < r1; ++r) {
+                uint32_t* c = p.matrix + (int64_t)r * nl + leaf;
+                const uint32_t t = *c;
+                *c = run;
+                run += t;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(C) ms_scatter_kernel(const MsParams p) {
+    extern __shared__ int32_t smem_ms[];
+    if (p.header[G2PC_HDR_POISON] != 0) return;
+    const int nl = p.header[G2PC_HDR_NUM_LEAVES];
+    constexpr int WORDS = C / 32;
+    QtTables T;
+    int32_t* s_leaf = ms_load_common(p, smem_ms, T);
+    uint32_t* s_gid = reinterpret_cast<uint32_t*>(s_leaf + (1 << (2 * p.base_level)));
+    uint32_t* s_bits = s_gid + C;  // [WORDS][nl]
+    for (int i = threadIdx.x; i < WORDS * nl; i += C) s_bits[i] = 0u;
+    __syncthreads();
+    const int64_t k = (int64_t)blockIdx.x * C + threadIdx.x;
+    if (k < p.n) {
+        const unsigned long long v = p.val_sorted[k];
+        s_gid[threadIdx.x] = (uint32_t)v;
+        const uint32_t bit = 1u << (threadIdx.x & 31);
+        uint32_t* rowbits = s_bits + (threadIdx.x >> 5) * nl;
+        for_each_leaf(p, T, s_leaf, (uint32_t)(v >> 32), (uint32_t)v, [&](int leaf) { atomicOr(rowbits + leaf, bit); });
+    }
+    __syncthreads();
+    const uint32_t* row = p.matrix + (int64_t)blockIdx.x * nl;
+    for (int leaf = threadIdx.x; leaf < nl; leaf += C) {
+        uint32_t pos = row[leaf];
+#pragma unroll
+        for (int w = 0; w < WORDS; ++w) {
+            uint32_t word = s_bits[w * nl + leaf];
+            while (word) {
+                const int b = __ffs(word) - 1;
+                word &= word - 1u;
+                p.inst_gid[pos++] = s_gid[w * 32 + b];
+            }
+        }
+    }
+}
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+template <int C>
+int launch_multisplit(const MsParams& p, int32_t chunks, cudaStream_t st) {
+    const size_t common = ((size_t)6 * p.n1 + ((size_t)1 << (2 * p.base_level))) * sizeof(int32_t);
+    const size_t smem_count = common + (size_t)p.leaf_cap * sizeof(uint32_t);
+    const size_t smem_scatter = common + ((size_t)C + (size_t)(C / 32) * p.leaf_cap) * sizeof(uint32_t);
+    if (smem_scatter > 200 * 1024) { g2pc_set_error("g2pc_multisplit: shared memory budget exceeded"); return G2PC_ERR_INVALID; }
+    if (smem_count > 48 * 1024)
+        G2PC_CUDA(cudaFuncSetAttribute(ms_count_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
+    if (smem_scatter > 48 * 1024)
+        G2PC_CUDA(cudaFuncSetAttribute(ms_scatter_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
+    ms_count_kernel<C><<<(unsigned)chunks, C, smem_count, st>>>(p);
+    G2PC_CHECK_LAUNCH();
+    const int scan_grid = (p.leaf_cap + 31) / 32;
+    ms_scan_kernel<<<(unsigned)(scan_grid < 1 ? 1 : scan_grid), 1024, 0, st>>>(p, chunks);
+    G2PC_CHECK_LAUNCH();
+    ms_scatter_kernel<C><<<(unsigned)chunks, C, smem_scatter, st>>>(p);
+    G2PC_CHECK_LAUNCH();
+    return G2PC_OK;
 }
 
 }  // namespace
 
 extern "C" int g2pc_build_tree(const int32_t* tables, int32_t num_levels, int32_t max_gaussians_per_tile,
-                               const uint32_t* node_cnt, const uint32_t* incl, int64_t n, uint8_t* node_state,
-                               int32_t* leaf_of_node, g2pc_leaf_t* leaves, int32_t* seg_begin, int32_t* leaf_order,
-                               int32_t max_leaves, int32_t* header, void* stream) {
-    G2PC_CHECK_ARG(tables && node_cnt && node_state && leaf_of_node && leaves && seg_begin && leaf_order && header,
+                               uint32_t* node_cnt, uint8_t* node_state, int32_t* node_leaf, g2pc_leaf_t* leaves,
+                               int32_t* leaf_order, int32_t max_leaves, int64_t inst_capacity, int64_t pix_capacity,
+                               int64_t matrix_capacity, int32_t ms_chunks, int32_t frame, int32_t* header,
+                               int32_t* work_counters, void* stream) {
+    G2PC_CHECK_ARG(tables && node_cnt && node_state && node_leaf && leaves && leaf_order && header && work_counters,
                    "null pointer");
     G2PC_CHECK_ARG(num_levels >= 1 && num_levels <= G2PC_MAX_LEVELS && max_leaves >= 1, "bad sizes");
+    G2PC_CHECK_ARG(frame >= 0 && ms_chunks >= 0, "bad frame / chunk count");
     TreeParams p;
     p.meta.num_levels = num_levels; p.meta.max_gaussians_per_tile = max_gaussians_per_tile;
     p.meta.width = 0; p.meta.height = 0;
     p.n1 = (1 << num_levels) - 1;
     p.tab.xs = tables; p.tab.xe = tables + p.n1; p.tab.xf = tables + 2 * p.n1;
     p.tab.ys = tables + 3 * p.n1; p.tab.ye = tables + 4 * p.n1; p.tab.yf = tables + 5 * p.n1;
-    p.node_cnt = node_cnt; p.node_state = node_state; p.leaf_of_node = leaf_of_node; p.leaves = leaves;
-    p.seg_begin = seg_begin; p.leaf_order = leaf_order; p.max_leaves = max_leaves; p.incl = incl; p.n = n;
-    p.header = header;
+    p.node_cnt = node_cnt; p.node_state = node_state; p.node_leaf = node_leaf; p.leaves = leaves;
+    p.leaf_order = leaf_order; p.max_leaves = max_leaves;
+    p.inst_capacity = inst_capacity; p.pix_capacity = pix_capacity; p.matrix_capacity = matrix_capacity;
+    p.ms_chunks = ms_chunks; p.frame = frame; p.header = header; p.work_counters = work_counters;
+    p.nodes_2d = ((1 << (2 * num_levels)) - 1) / 3;
     tree_kernel<<<1, TB, 0, (cudaStream_t)stream>>>(p);
     G2PC_CHECK_LAUNCH();
     return G2PC_OK;
 }
 
-namespace {
-struct GatherTouched {
-    const uint32_t* touched;
-    const uint32_t* order;
-    __host__ __device__ __forceinline__ uint32_t operator()(const int64_t k) const { return touched[order[k]]; }
-};
-__global__ void iota_kernel(uint32_t* v, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v[i] = (uint32_t)i;
-}
-size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-}  // namespace
-
-// workspace layout of g2pc_depth_order: [keys_out n u32][iota n u32][cub temp]
-extern "C" int64_t g2pc_depth_order_workspace_bytes(int64_t n) {
-    size_t sort_b = 0, scan_b = 0;
+// workspace layout of g2pc_depth_sort: [keys_out n u32][cub temp]
+extern "C" int64_t g2pc_depth_sort_workspace_bytes(int64_t n) {
+    size_t sort_b = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_b, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, n);
-    GatherTouched op{nullptr, nullptr};
-    auto it = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), op);
-    cub::DeviceScan::InclusiveSum(nullptr, scan_b, it, (uint32_t*)nullptr, n);
-    return (int64_t)(2 * align256((size_t)n * 4) + align256(sort_b > scan_b ? sort_b : scan_b));
+                                    (const unsigned long long*)nullptr, (unsigned long long*)nullptr, n);
+    return (int64_t)(align256((size_t)n * 4) + align256(sort_b));
 }
 
-/* Sort the Gaussians by depth key (stable: ties keep index order) -> order[k]; then incl[k] = inclusive prefix sum of
- * touched[order[k]]. */
-extern "C" int g2pc_depth_order(const uint32_t* depth_key, const uint32_t* touched, int64_t n, uint32_t* order,
-                                uint32_t* incl, void* workspace, int64_t workspace_bytes, void* stream) {
+/* Sort the (depth key, value) pairs by key (stable: ties keep index order) -> val_sorted[k] = value of the k-th nearest
+ * Gaussian. */
+extern "C" int g2pc_depth_sort(const uint32_t* depth_key, const uint64_t* val, int64_t n, uint64_t* val_sorted,
+                               void* workspace, int64_t workspace_bytes, void* stream) {
     G2PC_CHECK_ARG(n >= 0, "n < 0");
     if (n == 0) return G2PC_OK;
-    G2PC_CHECK_ARG(depth_key && touched && order && incl && workspace, "null pointer");
-    G2PC_CHECK_ARG(workspace_bytes >= g2pc_depth_order_workspace_bytes(n), "workspace too small");
-    cudaStream_t st = (cudaStream_t)stream;
+    G2PC_CHECK_ARG(depth_key && val && val_sorted && workspace, "null pointer");
+    G2PC_CHECK_ARG(workspace_bytes >= g2pc_depth_sort_workspace_bytes(n), "workspace too small");
     char* ws = (char*)workspace;
     uint32_t* keys_out = (uint32_t*)ws;
-    uint32_t* iota = (uint32_t*)(ws + align256((size_t)n * 4));
-    void* tmp = ws + 2 * align256((size_t)n * 4);
-    size_t tmp_b = (size_t)workspace_bytes - 2 * align256((size_t)n * 4);
-    iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(iota, n);
-    G2PC_CHECK_LAUNCH();
-    size_t b = tmp_b;
-    G2PC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, b, depth_key, keys_out, (const uint32_t*)iota, order, n, 0, 32, st));
-    GatherTouched op{touched, order};
-    auto it = thrust::make_transform_iterator(thrust::counting_iterator<int64_t>(0), op);
-    b = tmp_b;
-    G2PC_CUDA(cub::DeviceScan::InclusiveSum(tmp, b, it, incl, n, st));
+    void* tmp = ws + align256((size_t)n * 4);
+    size_t b = (size_t)workspace_bytes - align256((size_t)n * 4);
+    G2PC_CUDA(cub::DeviceRadixSort::SortPairs(tmp, b, depth_key, keys_out, (const unsigned long long*)val,
+                                              (unsigned long long*)val_sorted, n, 0, 32, (cudaStream_t)stream));
     return G2PC_OK;
 }
 
-extern "C" int64_t g2pc_sort_instances_workspace_bytes(int64_t num_items) {
-    size_t bytes = 0;
-    cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
-    if (cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, num_items, 0, 32) != cudaSuccess) return -1;
-    return (int64_t)bytes;
+extern "C" int32_t g2pc_multisplit_chunk(int32_t leaf_cap) {
+    // entries per chunk: the scatter kernel keeps leaf_cap x chunk bits in shared memory
+    if ((int64_t)leaf_cap * 32 <= 160 * 1024) return 256;
+    if ((int64_t)leaf_cap * 16 <= 160 * 1024) return 128;
+    if ((int64_t)leaf_cap * 8 <= 160 * 1024) return 64;
+    return 0;
 }
 
-/* Stable radix sort of the (leaf id, gid) instance pairs on the low `leaf_bits` bits of the leaf id (padding entries
- * carry 0xFFFFFFFF and sort to the end).  *sorted_in_alt_host = 1 if the result ended in the *_alt buffers. */
-extern "C" int g2pc_sort_instances(uint32_t* inst_leaf, uint32_t* inst_leaf_alt, uint32_t* inst_gid,
-                                   uint32_t* inst_gid_alt, int64_t num_items, int32_t leaf_bits, void* workspace,
-                                   int64_t workspace_bytes, int32_t* sorted_in_alt_host, void* stream) {
-    G2PC_CHECK_ARG(num_items >= 0 && leaf_bits >= 1 && leaf_bits <= 32, "bad sizes");
-    if (sorted_in_alt_host) *sorted_in_alt_host = 0;
-    if (num_items == 0) return G2PC_OK;
-    G2PC_CHECK_ARG(inst_leaf && inst_leaf_alt && inst_gid && inst_gid_alt && workspace && sorted_in_alt_host,
-                   "null pointer");
-    cub::DoubleBuffer<uint32_t> k(inst_leaf, inst_leaf_alt), v(inst_gid, inst_gid_alt);
-    size_t bytes = (size_t)workspace_bytes;
-    G2PC_CUDA(cub::DeviceRadixSort::SortPairs(workspace, bytes, k, v, num_items, 0, leaf_bits, (cudaStream_t)stream));
-    *sorted_in_alt_host = (v.Current() == inst_gid_alt) ? 1 : 0;
-    return G2PC_OK;
+extern "C" int g2pc_multisplit(const uint64_t* val_sorted, int64_t n, const void* proj, int32_t width, int32_t height,
+                               const int32_t* tables, int32_t num_levels, uint32_t level_mask, const int32_t* node_leaf,
+                               const g2pc_leaf_t* leaves, const int32_t* header, int32_t leaf_cap, uint32_t* matrix,
+                               uint32_t* inst_gid, void* stream) {
+    G2PC_CHECK_ARG(n >= 0, "n < 0");
+    if (n == 0) return G2PC_OK;
+    G2PC_CHECK_ARG(val_sorted && proj && tables && node_leaf && leaves && header && matrix && inst_gid, "null pointer");
+    G2PC_CHECK_ARG(num_levels >= 1 && num_levels <= G2PC_MAX_LEVELS && level_mask != 0u, "bad levels");
+    const int C = g2pc_multisplit_chunk(leaf_cap);
+    G2PC_CHECK_ARG(C > 0, "too many leaves for the multisplit");
+    MsParams p;
+    p.val_sorted = (const unsigned long long*)val_sorted; p.n = n; p.proj = (const float4*)proj;
+    p.width = width; p.height = height;
+    p.meta.num_levels = num_levels; p.meta.max_gaussians_per_tile = 0; p.meta.width = width; p.meta.height = height;
+    p.n1 = (1 << num_levels) - 1;
+    p.tab.xs = tables; p.tab.xe = tables + p.n1; p.tab.xf = tables + 2 * p.n1;
+    p.tab.ys = tables + 3 * p.n1; p.tab.ye = tables + 4 * p.n1; p.tab.yf = tables + 5 * p.n1;
+    p.level_mask = level_mask; p.base_level = __builtin_ctz(level_mask);
+    G2PC_CHECK_ARG(p.base_level <= G2PC_RANGE_MAX_LEVEL, "first leaf-candidate level too deep");
+    p.node_leaf = node_leaf; p.header = header; p.leaves = leaves; p.matrix = matrix; p.inst_gid = inst_gid;
+    p.leaf_cap = leaf_cap;
+    const int32_t chunks = (int32_t)((n + C - 1) / C);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 256) return launch_multisplit<256>(p, chunks, st);
+    if (C == 128) return launch_multisplit<128>(p, chunks, st);
+    return launch_multisplit<64>(p, chunks, st);
 }

@@ -34,20 +34,19 @@ SIGNATURES = {
     "g2pc_sample_emit": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p, _i32, _u64, _u32, _c_void_p,
                           _c_void_p, _c_void_p, ctypes.c_int, _i64, _c_void_p], ctypes.c_int),
     "g2pc_dump_eps": ([_c_void_p, _i64, _i32, _i32, _u64, _u32, _c_void_p, _c_void_p], ctypes.c_int),
-    "g2pc_preprocess": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i32, _i32, _i64, _c_void_p, _c_void_p,
-                         _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
-    "g2pc_depth_order_workspace_bytes": ([_i64], ctypes.c_int64),
-    "g2pc_depth_order": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p, _i64, _c_void_p], ctypes.c_int),
-    "g2pc_build_tree": ([_c_void_p, _i32, _i32, _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
-                         _c_void_p, _i32, _c_void_p, _c_void_p], ctypes.c_int),
-    "g2pc_emit_instances": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _i64, _i32, _i32, _c_void_p, _i32, _u32,
-                             _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
-    "g2pc_sort_instances_workspace_bytes": ([_i64], ctypes.c_int64),
-    "g2pc_sort_instances": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _i64, _i32, _c_void_p, _i64, _c_void_p,
-                             _c_void_p], ctypes.c_int),
-    "g2pc_blend": ([_c_void_p, _c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
-                    _i32, _i32, _f32, _c_void_p, _c_void_p], ctypes.c_int),
-    "g2pc_accumulate": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_pack_geometry": ([_c_void_p, _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_preprocess": ([_c_void_p, _c_void_p, _c_void_p, _i32, _i32, _i64, _c_void_p, _c_void_p, _i32, _u32, _c_void_p,
+                         _c_void_p, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_depth_sort_workspace_bytes": ([_i64], ctypes.c_int64),
+    "g2pc_depth_sort": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _i64, _c_void_p], ctypes.c_int),
+    "g2pc_build_tree": ([_c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i32, _i64, _i64,
+                         _i64, _i32, _i32, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_multisplit_chunk": ([_i32], ctypes.c_int32),
+    "g2pc_multisplit": ([_c_void_p, _i64, _c_void_p, _i32, _i32, _c_void_p, _i32, _u32, _c_void_p, _c_void_p, _c_void_p,
+                         _i32, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_blend": ([_c_void_p, _c_void_p, _c_void_p, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                    _c_void_p, _i32, _i32, _f32, _f32, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_accumulate": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p, _i32, _c_void_p], ctypes.c_int),
     "g2pc_compose_image": ([_c_void_p, _c_void_p, _i32, _i32, _f32, _c_void_p, _c_void_p], ctypes.c_int),
 }
 
@@ -58,8 +57,11 @@ class Camera(ctypes.Structure):
                 ("tan_fovy", _f32), ("focal_x", _f32), ("focal_y", _f32), ("width", _i32), ("height", _i32)]
 
 
-HDR_NUM_LEAVES, HDR_TOTAL_INST, HDR_TOTAL_PIX, HDR_NEED_DEEPER, HDR_LEAF_OVERFLOW, HDR_TOTAL_UPPER = 0, 1, 2, 3, 4, 5
-HDR_WORDS = 8
+(HDR_NUM_LEAVES, HDR_TOTAL_INST, HDR_TOTAL_PIX, HDR_NEED_DEEPER, HDR_LEAF_OVERFLOW, HDR_CAP_OVERFLOW, HDR_POISON,
+ HDR_FRAME, HDR_TOTAL_INST_HI) = range(9)
+HDR_WORDS = 16
+WORK_COUNTERS = 4
+STAT_WARP_GAUSSIANS, STAT_WORDS = 0, 4
 LEAF_WORDS = 8  # g2pc_leaf_t = 8 x int32
 
 _lib = None
@@ -89,9 +91,12 @@ def load(path=None):
 
 
 # ---- launch accounting (bench.py reads these) -------------------------------------------------------------------
-LAUNCHES = 0      # number of g2pc kernel entry points invoked since the last reset
-TIMING = None     # None, or {entry point name: [(start_event, end_event), ...]} to time launches with CUDA events
-_NOT_KERNELS = {"g2pc_version", "g2pc_last_error", "g2pc_sample_emit_chunk_points"}
+LAUNCHES = 0      # number of hand-written g2pc kernels launched since the last reset
+TIMING = None     # None, or a dict filled as {entry point name: [(start_event, end_event), ...]}: every launch is
+                  # bracketed with CUDA events on the current stream (bench.py)
+# hand-written kernels launched per entry point (default 1); the radix sort inside g2pc_depth_sort is cub's (library)
+_OWN_KERNELS = {"g2pc_multisplit": 3, "g2pc_depth_sort": 0}
+_NOT_KERNELS = {"g2pc_version", "g2pc_last_error", "g2pc_sample_emit_chunk_points", "g2pc_multisplit_chunk"}
 
 
 def call(name, *args):
@@ -99,15 +104,15 @@ def call(name, *args):
     dict — bracket it with CUDA events on the current stream."""
     global LAUNCHES
     fn = getattr(load(), name)
-    if TIMING is not None and name in TIMING:
+    if TIMING is not None and name not in _NOT_KERNELS:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         status = fn(*args)
         b.record()
-        TIMING[name].append((a, b))
+        TIMING.setdefault(name, []).append((a, b))
     else:
         status = fn(*args)
-    LAUNCHES += 1
+    LAUNCHES += _OWN_KERNELS.get(name, 1)
     check(status, name)
 
 

@@ -22,3 +22,10 @@ ATTEMPTS_STORED_FIRST = 16
 # (gauss_render.py:266).
 MAX_TILE_SIZE = 60
 MAX_GAUSSIANS_PER_TILE = 60000
+
+# Transmittance below which a warp of the blend kernel stops walking its tile's list (all of its 128 pixels must be
+# below it).  Every skipped contribution is then < BLEND_T_STOP and so is their sum per pixel, i.e. colours, images and
+# per-Gaussian maximum contributions move by less than 1e-6 (the parity contract is 1e-4).  0 selects FLT_MIN: only
+# contributions that underflow are dropped (the strict-parity tests use it).  The reference's CUDA back-end stops each
+# pixel at T < 1e-4 (forward.cu:415); its python back-end never stops.
+BLEND_T_STOP = 1e-6

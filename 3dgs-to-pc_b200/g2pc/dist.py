@@ -155,18 +155,18 @@ def convert_gaussians_to_pc_sharded(scene, transforms, intrinsics, settings, ren
                                 gaussians.colours, gaussians.covariances, shs=gaussians.shs if render_shs else None,
                                 visible_gaussian_threshold=s.visibility_threshold)
         names = list(transforms.keys())
+        # the accumulate kernel records the index of the camera that raised each maximum (needed by the merge)
         first_cam = torch.full((n_all,), torch.iinfo(torch.int32).max, dtype=torch.int32, device=keep.device)
-        prev = renderer.gaussian_max_contribution.clone()
+        renderer.first_frame = first_cam
+        renderer.async_mode = True
         for ci in camera_shard(len(names)):
             name = names[ci]
             tr = transforms[name]
             tr = torch.as_tensor(tr, dtype=torch.float32) if not torch.is_tensor(tr) else tr
             cam = get_camera(s.renderer_type, tr, intrinsics[name], colour_resolution=s.colour_resolution,
                              sh_degree=s.max_sh_degree, white_bkgd=True, mask=None)
-            renderer(cam)
-            improved = renderer.gaussian_max_contribution > prev
-            first_cam[improved] = ci
-            prev.copy_(renderer.gaussian_max_contribution)
+            renderer(cam, camera_index=ci)
+        renderer.flush()
         merge_colour_accumulators(renderer.gaussian_max_contribution, renderer.gaussian_colours, first_cam)
         gaussians.colours = renderer.get_gaussian_colours()
         if s.remove_unrendered_gaussians:
@@ -175,6 +175,7 @@ def convert_gaussians_to_pc_sharded(scene, transforms, intrinsics, settings, ren
             keep &= gaussians.opacities > s.min_opacity
         if s.prioritise_visible_gaussians:
             contributions = renderer.get_total_gaussian_contributions()
+        g2p.LAST_RENDER_STATS = {"stats": renderer._stats, "replays": renderer.replays}
         del renderer
     else:
         gaussians.colours = gaussians.colours * 255

@@ -7,8 +7,8 @@ getters used by the pipeline (gauss_to_pc.py:481-513).
 
 `renderer_type="python"` reproduces GaussPythonRenderer (:210-465): quadtree tiles, every Gaussian of a tile blended
 into every pixel of the tile — but as sm_100a kernels behind the C ABI (csrc/s3_preprocess.cu, s4_tree.cu,
-s5_blend.cu), one camera = 9 entry-point calls + one 32-byte header read.  The tile parameters the reference derives from free
-GPU memory at call time (:440-444) are pinned (g2pc.config.MAX_TILE_SIZE / MAX_GAUSSIANS_PER_TILE).
+s5_blend.cu), one camera = 8 asynchronous entry-point calls and no host wait.  The tile parameters the reference derives
+from free GPU memory at call time (:440-444) are pinned (g2pc.config.MAX_TILE_SIZE / MAX_GAUSSIANS_PER_TILE).
 """
 import ctypes
 import math
@@ -36,7 +36,15 @@ def strip_symmetric(sym):
 
 class GaussPythonRenderer():
     """B200 implementation of the reference's pure-torch tile renderer (same constructor arguments, attributes and
-    getters as gauss_render.py:210-264)."""
+    getters as gauss_render.py:210-264).
+
+    One camera ("frame") = 8 asynchronous entry-point calls and NO host wait: every size the later kernels need lives
+    in a device-side frame header.  The host sizes its buffers optimistically; a frame that does not fit (or needs a
+    deeper quadtree table) poisons the header on the device, every later kernel becomes a no-op, and the host — which
+    reads the 64-byte headers back asynchronously — grows the buffers and replays from the failed frame, so the
+    accumulators are updated in exactly the reference's camera order.  `async_mode = False` (default) confirms every
+    frame before returning (the returned image is final); the pipeline driver sets `async_mode = True` and confirms
+    lazily (getters call flush())."""
 
     def __init__(self, means3D, opacity, colour, cov3d, white_bkgd=True, visible_gaussian_threshold=0.0, shs=None,
                  sh_degree=None):
@@ -45,11 +53,12 @@ class GaussPythonRenderer():
         self.white_bkgd = white_bkgd
         self.device = means3D.device
         n = means3D.shape[0]
+        dev = self.device
 
-        self.gaussian_max_contribution = torch.zeros(n, device=self.device, dtype=torch.float32)
-        self.gaussian_total_contribution = torch.zeros(n, device=self.device, dtype=torch.float32)
+        self.gaussian_max_contribution = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.gaussian_total_contribution = torch.zeros(n, device=dev, dtype=torch.float32)
         # blended colour of each Gaussian's best pixel (f32; the reference keeps f64)
-        self.gaussian_colours = torch.zeros((n, 3), device=self.device, dtype=torch.float32)
+        self.gaussian_colours = torch.zeros((n, 3), device=dev, dtype=torch.float32)
         self.visible_gaussian_threshold = visible_gaussian_threshold
 
         self.means3D = means3D.to(torch.float32).contiguous()
@@ -67,40 +76,64 @@ class GaussPythonRenderer():
 
         self.max_tile_size = config.MAX_TILE_SIZE
         self.max_gaussians_per_tile = config.MAX_GAUSSIANS_PER_TILE
+        self.t_stop = config.BLEND_T_STOP
         self.compose_image = True
+        self.async_mode = False
+        self.first_frame = None  # optional (n) int32: index of the camera that raised each maximum (g2pc/dist.py)
         self._tables = {}
         self._extra_levels = 0
         self._n = n
+        st = capi.stream_ptr(dev)
+        # packed geometry, read by every camera with 16-byte loads (once per renderer)
+        self._geom = torch.empty((max(n, 1), 12), dtype=torch.float32, device=dev)
+        capi.call("g2pc_pack_geometry", capi.ptr(self.means3D), capi.ptr(self.cov3d), capi.ptr(self.opacity), n,
+                  capi.ptr(self._geom), st)
         # per-camera scratch, allocated once
-        self._proj = torch.empty((n, 12), dtype=torch.float32, device=self.device)
-        self._cam_best = torch.zeros((n,), dtype=torch.int64, device=self.device)
-        self._depth_key = torch.empty((n,), dtype=torch.int32, device=self.device)
-        self._touched = torch.empty((n,), dtype=torch.int32, device=self.device)
-        self._order = torch.empty((n,), dtype=torch.int32, device=self.device)
-        self._incl = torch.empty((n,), dtype=torch.int32, device=self.device)
-        self._depth_ws = None
-        self._inst_leaf = self._inst_leaf_alt = self._inst_gid = self._inst_gid_alt = None
+        self._proj = torch.empty((max(n, 1), 12), dtype=torch.float32, device=dev)
+        self._cam_best = torch.zeros((max(n, 1),), dtype=torch.int64, device=dev)
+        self._depth_key = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+        self._val = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
+        self._val_sorted = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
+        nbytes = self.lib.g2pc_depth_sort_workspace_bytes(max(n, 1))
+        self._depth_ws = torch.empty((max(int(nbytes), 1),), dtype=torch.uint8, device=dev)
+        self._hdr = torch.zeros((capi.HDR_WORDS,), dtype=torch.int32, device=dev)
+        self._work = torch.zeros((capi.WORK_COUNTERS,), dtype=torch.int32, device=dev)
+        self._stats = torch.zeros((capi.STAT_WORDS,), dtype=torch.int64, device=dev)
+        self._inst_gid = None
         self._leaf_colour = None
-        self._sort_ws = None
-        self._hdr_host = torch.zeros((capi.HDR_WORDS,), dtype=torch.int32).pin_memory()
+        self._matrix = None
+        self._inst_cap = max(8 * n, 1 << 16)
+        self._frame = 0
+        self._pending = []   # frames enqueued but not yet confirmed: (frame, camera, camera_index, pinned header, event)
+        self._hdr_pool = []
+        self.replays = 0
         self.last_stats = {}
 
     # ---- getters (gauss_render.py:237-264) -----------------------------------------------------------------
     def get_gaussian_colours(self):
+        self.flush()
         return self.gaussian_colours * 255
 
     def get_gaussians_above_contribution_threshold(self, contribution_threshold):
+        self.flush()
         return self.gaussian_max_contribution > contribution_threshold
 
     def get_visible_gaussians(self):
         return self.get_gaussians_above_contribution_threshold(self.visible_gaussian_threshold)
 
     def get_surface_gaussians(self):
+        self.flush()
         return self.get_gaussians_above_contribution_threshold(torch.mean(self.gaussian_max_contribution))
 
     def get_total_gaussian_contributions(self):
         # the python back-end of the reference reports the MAX contribution here (gauss_render.py:261-264)
+        self.flush()
         return self.gaussian_max_contribution
+
+    def executed_pairs(self):
+        """(pixel, Gaussian) pairs the blend kernel evaluated since construction (device counter)."""
+        self.flush()
+        return int(self._stats[capi.STAT_WARP_GAUSSIANS].item()) * 128
 
     # ---- per-resolution tables ---------------------------------------------------------------------------------
     def _get_tables(self, W, H):
@@ -111,21 +144,31 @@ class GaussPythonRenderer():
                                          extra_levels=self._extra_levels)
             flat = np.concatenate(qt.flat()).astype(np.int32)
             dev = self.device
-            t = dict(qt=qt, tables=torch.from_numpy(flat).to(dev),
-                     node_cnt=torch.zeros((qt.nodes_2d + 1,), dtype=torch.int32, device=dev),
+            mask = qt.candidate_level_mask()
+            base = (mask & -mask).bit_length() - 1
+            if base > 8:
+                raise capi.G2pcError("image too large for the packed node range (first leaf level deeper than 8)")
+            t = dict(qt=qt, tables=torch.from_numpy(flat).to(dev), level_mask=mask, base_level=base,
+                     node_cnt=torch.zeros((qt.nodes_2d,), dtype=torch.int32, device=dev),
                      node_state=torch.zeros((qt.nodes_2d,), dtype=torch.uint8, device=dev),
-                     leaf_of_node=torch.full((qt.nodes_2d,), -1, dtype=torch.int32, device=dev),
-                     leaves=torch.zeros((qt.nodes_2d, capi.LEAF_WORDS), dtype=torch.int32, device=dev),
-                     seg_begin=torch.zeros((qt.nodes_2d + 1,), dtype=torch.int32, device=dev),
-                     leaf_order=torch.zeros((qt.nodes_2d,), dtype=torch.int32, device=dev),
-                     header=torch.zeros((capi.HDR_WORDS,), dtype=torch.int32, device=dev),
+                     node_leaf=torch.full((qt.nodes_2d,), -1, dtype=torch.int32, device=dev),
                      owner=torch.zeros((W * H,), dtype=torch.int32, device=dev),
                      image=torch.ones((H, W, 3), dtype=torch.float32, device=dev),
-                     max_quads=int(max(((int(w) + 3) // 4) * int(h)
-                                       for w in [min(self.max_tile_size, W)] for h in [min(self.max_tile_size, H)])))
-            t["work_counter"] = t["node_cnt"][qt.nodes_2d:]  # zeroed together with the node counts
+                     leaf_cap=0, leaves=None, leaf_order=None, pix_cap=int(1.25 * W * H) + 4096,
+                     max_quads=int(((min(self.max_tile_size, W) + 3) // 4) * min(self.max_tile_size, H)))
+            self._set_leaf_cap(t, min(qt.nodes_2d, 2 * (4 ** base)))
             self._tables[key] = t
         return t
+
+    def _set_leaf_cap(self, t, cap):
+        cap = int(min(max(cap, 1), t["qt"].nodes_2d))
+        chunk = int(self.lib.g2pc_multisplit_chunk(cap))
+        if chunk <= 0:
+            raise capi.G2pcError(f"the quadtree has more than {cap} leaves: too many for the multisplit tables")
+        t["leaf_cap"], t["chunk"] = cap, chunk
+        t["chunks"] = (self._n + chunk - 1) // chunk
+        t["leaves"] = torch.zeros((cap, capi.LEAF_WORDS), dtype=torch.int32, device=self.device)
+        t["leaf_order"] = torch.zeros((cap,), dtype=torch.int32, device=self.device)
 
     @staticmethod
     def _camera_struct(camera):
@@ -150,104 +193,154 @@ class GaussPythonRenderer():
         c.height = camera.image_height
         return c
 
-    def _grow(self, name, numel, dtype):
-        buf = getattr(self, name)
-        if buf is None or buf.numel() < numel:
-            buf = torch.empty((int(numel * 1.25) + 1024,), dtype=dtype, device=self.device)
-            setattr(self, name, buf)
-        return buf
+    def _buffers(self, t):
+        """(Re)allocate the frame buffers for the current capacities."""
+        dev = self.device
+        need = self._inst_cap + 4 * t["leaf_cap"] + 64  # lists are padded to 16 bytes; slack for the last TMA unit
+        if self._inst_gid is None or self._inst_gid.numel() < need:
+            self._inst_gid = torch.empty((need,), dtype=torch.int32, device=dev)
+        if self._leaf_colour is None or self._leaf_colour.numel() < 3 * t["pix_cap"]:
+            self._leaf_colour = torch.empty((3 * t["pix_cap"],), dtype=torch.float32, device=dev)
+        mneed = t["chunks"] * t["leaf_cap"]
+        if self._matrix is None or self._matrix.numel() < mneed:
+            self._matrix = torch.empty((max(mneed, 1),), dtype=torch.int32, device=dev)
 
-    def __call__(self, camera, **kwargs):
-        """Render one camera and update the per-Gaussian accumulators (gauss_render.py:404-465).
-        Returns (image (H,W,3) f32 flipped left-right | None, None, None, None)."""
-        lib = self.lib
+    def _enqueue(self, camera, frame, camera_index):
+        """All kernels of one camera, asynchronously on the current stream."""
         st = capi.stream_ptr(self.device)
         W, H = int(camera.image_width), int(camera.image_height)
         cam = self._camera_struct(camera)
         n = self._n
-        if self._depth_ws is None:
-            nbytes = lib.g2pc_depth_order_workspace_bytes(n)
-            self._depth_ws = torch.empty((max(int(nbytes), 1),), dtype=torch.uint8, device=self.device)
-        while True:
-            t = self._get_tables(W, H)
-            qt = t["qt"]
-            t["node_cnt"].zero_()  # (work_counter is the last word of this buffer)
-            capi.call("g2pc_preprocess", capi.ptr(self.means3D), capi.ptr(self.cov3d), capi.ptr(self.opacity),
-                      capi.ptr(self._colour_f32) if self.shs is None else None, capi.ptr(self.shs),
-                      int(self.shs.shape[-1]) if self.shs is not None else 0, self.sh_degree, n, ctypes.byref(cam),
-                      capi.ptr(t["tables"]), qt.num_levels, qt.max_gaussians_per_tile, capi.ptr(self._proj),
-                      capi.ptr(t["node_cnt"]), capi.ptr(self._depth_key), capi.ptr(self._touched), st)
-            capi.call("g2pc_depth_order", capi.ptr(self._depth_key), capi.ptr(self._touched), n,
-                      capi.ptr(self._order), capi.ptr(self._incl), capi.ptr(self._depth_ws), self._depth_ws.numel(), st)
-            capi.call("g2pc_build_tree", capi.ptr(t["tables"]), qt.num_levels, qt.max_gaussians_per_tile,
-                      capi.ptr(t["node_cnt"]), capi.ptr(self._incl), n, capi.ptr(t["node_state"]),
-                      capi.ptr(t["leaf_of_node"]), capi.ptr(t["leaves"]), capi.ptr(t["seg_begin"]),
-                      capi.ptr(t["leaf_order"]), qt.nodes_2d, capi.ptr(t["header"]), st)
-            self._hdr_host.copy_(t["header"], non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()  # the one host read per camera (32 bytes)
-            hdr = self._hdr_host.tolist()
-            if hdr[capi.HDR_NEED_DEEPER]:
-                # a tile at the deepest tabulated level holds more than max_gaussians_per_tile Gaussians: tabulate one
-                # more level and redo this camera (rare; the reference keeps splitting in its host BFS)
-                self._extra_levels += 1
-                if self._get_tables(W, H)["qt"].num_levels <= qt.num_levels:
-                    raise capi.G2pcError(
-                        f"a tile still holds more than max_gaussians_per_tile={self.max_gaussians_per_tile} Gaussians at "
-                        f"quadtree level {qt.num_levels - 1} (tiles of a few pixels): deeper than the tabulated levels")
-                continue
-            if hdr[capi.HDR_LEAF_OVERFLOW]:
-                raise capi.G2pcError("leaf table overflow")
-            break
-        num_leaves, total_inst, total_pix = hdr[capi.HDR_NUM_LEAVES], hdr[capi.HDR_TOTAL_INST], hdr[capi.HDR_TOTAL_PIX]
-        total_upper = hdr[capi.HDR_TOTAL_UPPER]
-        self.last_stats = dict(num_leaves=num_leaves, total_instances=total_inst, total_leaf_pixels=total_pix,
-                               levels=qt.num_levels, instance_slots=total_upper)
+        t = self._get_tables(W, H)
+        qt = t["qt"]
+        self._buffers(t)
         bg = 1.0 if self.white_bkgd else 0.0
-        if num_leaves > 0 and total_inst > 0:
-            for name in ("_inst_leaf", "_inst_leaf_alt", "_inst_gid", "_inst_gid_alt"):
-                self._grow(name, total_upper, torch.int32)
-            leaf_colour = self._grow("_leaf_colour", total_pix * 3, torch.float32)
-            capi.call("g2pc_emit_instances", capi.ptr(self._proj), capi.ptr(self._order), capi.ptr(self._incl),
-                      capi.ptr(self._touched), n, W, H, capi.ptr(t["tables"]), qt.num_levels, qt.candidate_level_mask(),
-                      capi.ptr(t["node_state"]), capi.ptr(t["leaf_of_node"]), capi.ptr(self._inst_leaf),
-                      capi.ptr(self._inst_gid), st)
-            ws_bytes = lib.g2pc_sort_instances_workspace_bytes(total_upper)
-            if ws_bytes < 0:
-                raise capi.G2pcError("cub workspace query failed")
-            ws = self._grow("_sort_ws", max(ws_bytes, 1), torch.uint8)
-            in_alt = ctypes.c_int32(0)
-            # padding entries carry leaf id 0xFFFFFFFF: sorting on bit_length(num_leaves) bits puts them last
-            leaf_bits = max(1, int(num_leaves).bit_length())
-            capi.call("g2pc_sort_instances", capi.ptr(self._inst_leaf), capi.ptr(self._inst_leaf_alt),
-                      capi.ptr(self._inst_gid), capi.ptr(self._inst_gid_alt), total_upper, leaf_bits, capi.ptr(ws),
-                      ws.numel(), ctypes.byref(in_alt), st)
-            sorted_gid = self._inst_gid_alt if in_alt.value else self._inst_gid
-            self._last_sorted_gid = sorted_gid
-            capi.call("g2pc_blend", capi.ptr(t["leaves"]), capi.ptr(t["leaf_order"]), num_leaves, t["max_quads"],
-                      capi.ptr(sorted_gid), capi.ptr(self._proj), capi.ptr(self._cam_best),
-                      capi.ptr(self.gaussian_max_contribution), capi.ptr(leaf_colour), capi.ptr(t["owner"]), W, H, bg,
-                      capi.ptr(t["work_counter"]), st)
-            capi.call("g2pc_accumulate", capi.ptr(self._cam_best), capi.ptr(leaf_colour), n,
-                      capi.ptr(self.gaussian_max_contribution), capi.ptr(self.gaussian_colours), st)
-            if self.compose_image:
-                capi.call("g2pc_compose_image", capi.ptr(t["owner"]), capi.ptr(leaf_colour), W, H, bg,
-                          capi.ptr(t["image"]), st)
-            else:
-                t["owner"].zero_()
-        elif self.compose_image:
-            t["image"].fill_(bg)
+        capi.call("g2pc_preprocess", capi.ptr(self._geom), capi.ptr(self._colour_f32) if self.shs is None else None,
+                  capi.ptr(self.shs), int(self.shs.shape[-1]) if self.shs is not None else 0, self.sh_degree, n,
+                  ctypes.byref(cam), capi.ptr(t["tables"]), qt.num_levels, t["level_mask"], capi.ptr(self._proj),
+                  capi.ptr(t["node_cnt"]), capi.ptr(self._depth_key), capi.ptr(self._val), st)
+        capi.call("g2pc_depth_sort", capi.ptr(self._depth_key), capi.ptr(self._val), n, capi.ptr(self._val_sorted),
+                  capi.ptr(self._depth_ws), self._depth_ws.numel(), st)
+        capi.call("g2pc_build_tree", capi.ptr(t["tables"]), qt.num_levels, qt.max_gaussians_per_tile,
+                  capi.ptr(t["node_cnt"]), capi.ptr(t["node_state"]), capi.ptr(t["node_leaf"]), capi.ptr(t["leaves"]),
+                  capi.ptr(t["leaf_order"]), t["leaf_cap"], self._inst_cap, t["pix_cap"], self._matrix.numel(),
+                  t["chunks"], frame, capi.ptr(self._hdr), capi.ptr(self._work), st)
+        capi.call("g2pc_multisplit", capi.ptr(self._val_sorted), n, capi.ptr(self._proj), W, H, capi.ptr(t["tables"]),
+                  qt.num_levels, t["level_mask"], capi.ptr(t["node_leaf"]), capi.ptr(t["leaves"]), capi.ptr(self._hdr),
+                  t["leaf_cap"], capi.ptr(self._matrix), capi.ptr(self._inst_gid), st)
+        capi.call("g2pc_blend", capi.ptr(t["leaves"]), capi.ptr(t["leaf_order"]), capi.ptr(self._hdr), t["max_quads"],
+                  capi.ptr(self._inst_gid), capi.ptr(self._proj), capi.ptr(self._cam_best),
+                  capi.ptr(self.gaussian_max_contribution), capi.ptr(self._leaf_colour), capi.ptr(t["owner"]), W, H, bg,
+                  float(self.t_stop), capi.ptr(self._work), capi.ptr(self._stats), st)
+        capi.call("g2pc_accumulate", capi.ptr(self._cam_best), capi.ptr(self._leaf_colour), n,
+                  capi.ptr(self.gaussian_max_contribution), capi.ptr(self.gaussian_colours),
+                  capi.ptr(self.first_frame), int(camera_index), st)
+        if self.compose_image:
+            capi.call("g2pc_compose_image", capi.ptr(t["owner"]), capi.ptr(self._leaf_colour), W, H, bg,
+                      capi.ptr(t["image"]), st)
+        else:
+            t["owner"].zero_()
         self._last_tables = t
-        return (t["image"] if self.compose_image else None), None, None, None
+        return t
 
+    def __call__(self, camera, camera_index=None, **kwargs):
+        """Render one camera and update the per-Gaussian accumulators (gauss_render.py:404-465).
+        Returns (image (H,W,3) f32 flipped left-right | None, None, None, None)."""
+        frame = self._frame
+        self._frame += 1
+        camera_index = frame if camera_index is None else camera_index
+        t = self._enqueue(camera, frame, camera_index)
+        hdr = self._hdr_pool.pop() if self._hdr_pool else torch.zeros((capi.HDR_WORDS,), dtype=torch.int32).pin_memory()
+        hdr.copy_(self._hdr, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._pending.append((frame, camera, camera_index, hdr, ev))
+        if not self.async_mode:
+            self.flush()
+        else:
+            self._poll(block_if_more_than=8)
+        if not self.compose_image:
+            return None, None, None, None
+        # confirmed frames get their own tensor, like the reference; in async mode the shared buffer is handed out (it is
+        # final once flush() has run and is overwritten by the next camera)
+        return (t["image"] if self.async_mode else t["image"].clone()), None, None, None
+
+    # ---- confirmation / recovery ---------------------------------------------------------------------------------
+    def _poll(self, block_if_more_than=None):
+        while self._pending:
+            frame, camera, cidx, hdr, ev = self._pending[0]
+            if not ev.query():
+                if block_if_more_than is None or len(self._pending) <= block_if_more_than:
+                    return
+                ev.synchronize()
+            h = hdr.tolist()
+            if h[capi.HDR_POISON]:
+                self._recover(h)
+                continue
+            self._confirm(h)
+            self._hdr_pool.append(hdr)
+            self._pending.pop(0)
+
+    def _confirm(self, h):
+        t = self._last_tables
+        self.last_stats = dict(num_leaves=h[capi.HDR_NUM_LEAVES],
+                               total_instances=h[capi.HDR_TOTAL_INST] + (h[capi.HDR_TOTAL_INST_HI] << 32),
+                               total_leaf_pixels=h[capi.HDR_TOTAL_PIX], levels=t["qt"].num_levels, frame=h[capi.HDR_FRAME])
+
+    def flush(self):
+        """Wait for every enqueued frame and replay the ones a poisoned header skipped."""
+        while self._pending:
+            self._pending[-1][4].synchronize()
+            self._poll(block_if_more_than=0)
+
+    def _recover(self, h):
+        """A frame did not fit: everything from that frame on was skipped on the device.  Grow, clear, replay."""
+        torch.cuda.current_stream(self.device).synchronize()
+        failed = h[capi.HDR_POISON] - 1
+        todo = [p for p in self._pending if p[0] >= failed]
+        self._pending = [p for p in self._pending if p[0] < failed]
+        t = self._last_tables
+        W, H = t["qt"].width, t["qt"].height
+        if h[capi.HDR_NEED_DEEPER]:
+            # a tile at the deepest tabulated level holds more than max_gaussians_per_tile Gaussians: tabulate one more
+            # level (rare; the reference keeps splitting in its host BFS)
+            levels = t["qt"].num_levels
+            self._extra_levels += 1
+            if self._get_tables(W, H)["qt"].num_levels <= levels:
+                raise capi.G2pcError(
+                    f"a tile still holds more than max_gaussians_per_tile={self.max_gaussians_per_tile} Gaussians at "
+                    f"quadtree level {levels - 1} (tiles of a few pixels): deeper than the tabulated levels")
+        elif h[capi.HDR_LEAF_OVERFLOW]:
+            if t["leaf_cap"] >= t["qt"].nodes_2d:
+                raise capi.G2pcError("leaf table overflow")
+            self._set_leaf_cap(t, max(2 * t["leaf_cap"], int(1.25 * h[capi.HDR_NUM_LEAVES])))
+        elif h[capi.HDR_CAP_OVERFLOW]:
+            total = h[capi.HDR_TOTAL_INST] + (h[capi.HDR_TOTAL_INST_HI] << 32)
+            if total > 0x7FFFFFFF:
+                raise capi.G2pcError(f"{total} (Gaussian, tile) instances in one camera: more than 2^31 - 1")
+            self._inst_cap = max(self._inst_cap, int(1.25 * total) + 1024)
+            t["pix_cap"] = max(t["pix_cap"], int(1.25 * h[capi.HDR_TOTAL_PIX]) + 1024)
+        else:
+            raise capi.G2pcError("poisoned frame header without a cause")
+        self._hdr.zero_()
+        for tt in self._tables.values():
+            tt["node_cnt"].zero_()
+        self.replays += 1
+        for (frame, camera, cidx, hdr, ev) in todo:
+            self._enqueue(camera, frame, cidx)
+            hdr.copy_(self._hdr, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._pending.append((frame, camera, cidx, hdr, ev))
 
     # ---- introspection for the parity tests ---------------------------------------------------------------------
     def debug_last_camera(self):
         """Per-Gaussian projection records and per-leaf sorted Gaussian ids of the most recent camera (host copies)."""
+        self.flush()
         t = self._last_tables
         nl = self.last_stats["num_leaves"]
         leaves = t["leaves"][:nl].cpu().numpy()
-        gids = (self._last_sorted_gid[: self.last_stats["total_instances"]].cpu().numpy().astype(np.int64)
-                if nl else np.zeros(0, np.int64))
+        gids = self._inst_gid.cpu().numpy().astype(np.int64) if nl else np.zeros(0, np.int64)
         out = []
         for (r0, c0, w, h, beg, cnt, pix, node) in leaves:
             out.append((int(r0), int(c0), int(w), int(h), gids[beg:beg + cnt]))

@@ -17,6 +17,7 @@ from camera_handler import get_camera
 from g2pc import capi, config, sampler
 
 LAST_SAMPLE_STATS = {}
+LAST_RENDER_STATS = {}
 COLOR_QUALITY_OPTIONS = {"tiny": 180, "low": 360, "medium": 720, "high": 1280, "ultra": 1920, "original": None}
 
 
@@ -287,8 +288,9 @@ def convert_gaussians_to_pc(xyz, scales, rots, colours, opacities, shs, transfor
                                          visible_gaussian_threshold=s.visibility_threshold,
                                          surface_distance_std=s.surface_distance_std,
                                          calculate_surface_distance=want_surface)
-        if not getattr(s, "keep_images", True) and hasattr(gaussian_renderer, "compose_image"):
-            gaussian_renderer.compose_image = False
+        # the driver never looks at the rendered images before the getters: let the renderer run ahead of the host
+        if hasattr(gaussian_renderer, "async_mode"):
+            gaussian_renderer.async_mode = True
 
         if transforms is None:
             raise Exception("Transforms are required to render colours")
@@ -331,6 +333,9 @@ def convert_gaussians_to_pc(xyz, scales, rots, colours, opacities, shs, transfor
         if s.prioritise_visible_gaussians:
             total_gaussian_contributions = gaussian_renderer.get_total_gaussian_contributions()[culled_indices]
 
+        global LAST_RENDER_STATS
+        LAST_RENDER_STATS = {"stats": getattr(gaussian_renderer, "_stats", None),
+                             "replays": getattr(gaussian_renderer, "replays", 0)}
         del gaussian_renderer
     else:
         gaussians.colours = gaussians.colours * 255

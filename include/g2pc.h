@@ -131,8 +131,9 @@ int g2pc_dump_eps(const int64_t* gids, int64_t n_gids, int32_t k, int32_t attemp
 /* ---- S3-S6: colour stage, renderer_type=python semantics (gauss_render.py:101-465) ------------------------------ */
 /* Replaces GaussPythonRenderer.__call__/render (gauss_render.py:266-465) and — as the native op boundary — the role
  * of _C.rasterize_gaussians (rasterize_points.cu:36-145) in the per-camera loop of gauss_to_pc.py:437-454.
- * One camera = preprocess -> depth_order -> build_tree -> [host reads the 32-byte header] -> emit_instances ->
- * sort_instances -> blend -> accumulate (-> compose_image). */
+ * One camera (a "frame") = preprocess -> depth_sort -> build_tree -> multisplit -> blend -> accumulate
+ * (-> compose_image).  No call waits for the device: every size the later stages need is read from the device-side
+ * frame header; a frame that does not fit the caller's buffers poisons the header (see G2PC_HDR_POISON). */
 typedef struct {
     float view[16];  /* world_view_transform, row-vector convention p_view = [p,1] * V (camera_handler.py:46), row-major */
     float proj[16];  /* projection_matrix as stored by Camera (already transposed, camera_handler.py:48), row-major */
@@ -143,88 +144,101 @@ typedef struct {
 
 typedef struct {
     int32_t r0, c0, w, h;    /* first row / column and size of the leaf tile in pixels */
-    int32_t inst_begin;      /* offset of the leaf's list in the sorted instance arrays */
+    int32_t inst_begin;      /* offset of the leaf's list in inst_gid */
     int32_t inst_count;      /* Gaussians whose rect overlaps the leaf */
     int32_t pix_offset;      /* offset of the leaf's pixels in the concatenated leaf-colour buffer */
     int32_t node;            /* index of the quadtree node */
 } g2pc_leaf_t;
 
 #define G2PC_MAX_LEVELS 12
-/* header words written by g2pc_build_tree (int32 each) */
+/* frame header (int32 words, device memory, written by g2pc_build_tree) */
 #define G2PC_HDR_NUM_LEAVES 0
-#define G2PC_HDR_TOTAL_INST 1    /* sum of the leaves' instance counts */
+#define G2PC_HDR_TOTAL_INST 1     /* sum of the leaves' instance counts, low word */
 #define G2PC_HDR_TOTAL_PIX 2
-#define G2PC_HDR_NEED_DEEPER 3   /* a tile at the deepest tabulated level still has to split: re-run with more levels */
-#define G2PC_HDR_LEAF_OVERFLOW 4 /* more leaves than max_leaves */
-#define G2PC_HDR_TOTAL_UPPER 5   /* instance slots emit_instances fills (>= TOTAL_INST; the rest is padding) */
-#define G2PC_HDR_WORDS 8
+#define G2PC_HDR_NEED_DEEPER 3    /* a tile at the deepest tabulated level still has to split: tabulate more levels */
+#define G2PC_HDR_LEAF_OVERFLOW 4  /* more leaves than max_leaves */
+#define G2PC_HDR_CAP_OVERFLOW 5   /* instance / leaf-pixel / multisplit-matrix capacity too small for this frame */
+#define G2PC_HDR_POISON 6         /* sticky: 1 + frame number of the first frame that failed; while non-zero
+                                     build_tree, multisplit, blend and accumulate do nothing (the caller clears the
+                                     word after growing its buffers and replays from that frame) */
+#define G2PC_HDR_FRAME 7          /* frame number of the header's contents */
+#define G2PC_HDR_TOTAL_INST_HI 8
+#define G2PC_HDR_WORDS 16
+#define G2PC_WORK_COUNTERS 4      /* int32 work-distribution counters cleared by g2pc_build_tree */
+/* device-side statistics (uint64 words, accumulated by g2pc_blend when `stats` is not NULL) */
+#define G2PC_STAT_WARP_GAUSSIANS 0  /* (warp, Gaussian) iterations executed: x 128 = (pixel, Gaussian) pairs */
+#define G2PC_STAT_WORDS 4
 
 /* Quadtree tables (host-built, g2pc/quadtree.py): `tables` = 6 int32 arrays of n1 = 2^num_levels - 1 entries each,
  * concatenated: x start, x end (inclusive), x flags, y start, y end, y flags; level l at offset 2^l - 1.
- * 2-D node index = (4^l - 1)/3 + iy * 2^l + ix. */
+ * 2-D node index = (4^l - 1)/3 + iy * 2^l + ix.  level_mask: bit l set iff level l has nodes small enough to be
+ * leaves (a node larger than max_tile_size splits whatever it holds; its count is never collected). */
+
+/* Once per renderer: geom (n x 48 bytes, 16-byte aligned) = {x,y,z,S00} {S01,S02,S11,S12} {S22,log2(opacity),0,0}
+ * from xyz (n,3), cov (n,3,3), opacity (n) — the coalesced 16-byte-load form the per-camera kernel reads. */
+int g2pc_pack_geometry(const float* xyz, const float* cov, const float* opacity, int64_t n, void* geom, void* stream);
 
 /* S3.  Per Gaussian: projection (projection_ndc, gauss_render.py:151-168), EWA covariance (build_covariance_2d
  * :101-148), radius / rect (:171-193), conic = inverse(cov2d) (:349) pre-scaled by -0.5*log2(e), colour (given, or SH
- * deg <= 3 evaluated towards the camera: eval_sh :43-99 + 0.5, clamped at 0), and tile-membership counting for every
- * tabulated level.  xyz (n,3) · cov (n,3,3) · opacity (n) · colours (n,3) f32 or NULL · shs (n,3,sh_stride) f32 channel-
- * major or NULL.  proj: n x 48 bytes (3 float4: {mx,my,c00',c01'} {c11',log2(opacity),r,g} {b,depth,radius,valid}).
- * node_cnt: one uint32 per 2-D node, zero-filled by the caller.  depth_key (n) uint32: bits(-z_view), 0xFFFFFFFF
- * if behind the camera.  touched (n) uint32: leaf-candidate nodes overlapped (upper bound of the instances). */
-int g2pc_preprocess(const float* xyz, const float* cov, const float* opacity, const float* colours,
-                    const float* shs, int32_t sh_stride, int32_t sh_degree, int64_t n,
-                    const g2pc_camera_t* cam_host, const int32_t* tables, int32_t num_levels,
-                    int32_t max_gaussians_per_tile, void* proj, uint32_t* node_cnt, uint32_t* depth_key,
-                    uint32_t* touched, void* stream);
+ * deg <= 3 evaluated towards the camera: eval_sh :43-99 + 0.5, clamped at 0), and tile-membership counting on the
+ * leaf-candidate levels.  colours (n,3) f32 or NULL · shs (n,3,sh_stride) f32 channel-major or NULL.
+ * proj: n x 48 bytes (3 float4: {mx,my,c00',c01'} {c11',log2(opacity),r,g} {b,depth,radius,valid}).
+ * node_cnt: one uint32 per 2-D node, zero on entry (g2pc_build_tree clears it again).  depth_key (n) uint32:
+ * bits(-z_view), 0xFFFFFFFF if behind the camera.  val (n) uint64: (node range at the first candidate level, 8 bits per
+ * bound: xlo | xhi<<8 | ylo<<16 | yhi<<24) << 32 | Gaussian index. */
+int g2pc_preprocess(const void* geom, const float* colours, const float* shs, int32_t sh_stride, int32_t sh_degree,
+                    int64_t n, const g2pc_camera_t* cam_host, const int32_t* tables, int32_t num_levels,
+                    uint32_t level_mask, void* proj, uint32_t* node_cnt, uint32_t* depth_key, uint64_t* val,
+                    void* stream);
 
-/* S4a.  order[k] = index of the k-th nearest Gaussian (stable radix sort of depth_key: ties keep index order, the
- * reference's torch.sort is unstable there, gauss_render.py:340-344); incl[k] = inclusive prefix sum of
- * touched[order[k]].  cub::DeviceRadixSort + cub::DeviceScan. */
-int64_t g2pc_depth_order_workspace_bytes(int64_t n);
-int g2pc_depth_order(const uint32_t* depth_key, const uint32_t* touched, int64_t n, uint32_t* order, uint32_t* incl,
-                     void* workspace, int64_t workspace_bytes, void* stream);
+/* S4a.  val_sorted[k] = val of the k-th nearest Gaussian (stable radix sort of depth_key: ties keep index order, the
+ * reference's torch.sort is unstable there, gauss_render.py:340-344).  cub::DeviceRadixSort (library call). */
+int64_t g2pc_depth_sort_workspace_bytes(int64_t n);
+int g2pc_depth_sort(const uint32_t* depth_key, const uint64_t* val, int64_t n, uint64_t* val_sorted, void* workspace,
+                    int64_t workspace_bytes, void* stream);
 
-/* S4b.  Resolve the quadtree (one CTA): node states, leaves in the reference's BFS order with instance / pixel
- * offsets, seg_begin[leaf] (max_leaves + 1 entries), leaf_order (heaviest leaf first, the blend's launch order),
- * header.  node_state: uint8 per node · leaf_of_node: int32 per node.  incl/n: from g2pc_depth_order (may be NULL/0). */
-int g2pc_build_tree(const int32_t* tables, int32_t num_levels, int32_t max_gaussians_per_tile,
-                    const uint32_t* node_cnt, const uint32_t* incl, int64_t n, uint8_t* node_state,
-                    int32_t* leaf_of_node, g2pc_leaf_t* leaves, int32_t* seg_begin, int32_t* leaf_order,
-                    int32_t max_leaves, int32_t* header, void* stream);
+/* S4b.  Resolve the quadtree (one CTA): node states, node_leaf (int32 per node: leaf id, -1 none, -2 split), leaves in
+ * the reference's BFS order with list / pixel offsets, leaf_order (heaviest leaf first, the blend's launch order), the
+ * frame header; clears node_cnt and work_counters.  inst_capacity (uint32 ids) / pix_capacity (pixels) /
+ * matrix_capacity (uint32 words, >= ms_chunks * leaves): sizes of the caller's buffers, checked here. */
+int g2pc_build_tree(const int32_t* tables, int32_t num_levels, int32_t max_gaussians_per_tile, uint32_t* node_cnt,
+                    uint8_t* node_state, int32_t* node_leaf, g2pc_leaf_t* leaves, int32_t* leaf_order,
+                    int32_t max_leaves, int64_t inst_capacity, int64_t pix_capacity, int64_t matrix_capacity,
+                    int32_t ms_chunks, int32_t frame, int32_t* header, int32_t* work_counters, void* stream);
 
-/* S4c.  In depth order: Gaussian order[k] writes (leaf id | 0xFFFFFFFF, Gaussian id) for every leaf-candidate node it
- * overlaps at slots [incl[k] - touched, incl[k]).  level_mask: bit l set iff level l has nodes that are not forced to
- * split by their size (levels without leaf candidates are skipped). */
-int g2pc_emit_instances(const void* proj, const uint32_t* order, const uint32_t* incl, const uint32_t* touched,
-                        int64_t n, int32_t width, int32_t height, const int32_t* tables, int32_t num_levels,
-                        uint32_t level_mask, const uint8_t* node_state, const int32_t* leaf_of_node,
-                        uint32_t* inst_leaf, uint32_t* inst_gid, void* stream);
-
-/* S4d.  Stable radix sort of the instance pairs on the low leaf_bits bits of the leaf id (cub::DeviceRadixSort): the
- * leaves' lists become contiguous ([seg_begin[l], seg_begin[l+1])) and stay depth-ordered.
- * *sorted_in_alt_host = 1 if the result ended in the *_alt buffers.  (The only entry point that writes a host word.) */
-int64_t g2pc_sort_instances_workspace_bytes(int64_t num_items);
-int g2pc_sort_instances(uint32_t* inst_leaf, uint32_t* inst_leaf_alt, uint32_t* inst_gid, uint32_t* inst_gid_alt,
-                        int64_t num_items, int32_t leaf_bits, void* workspace, int64_t workspace_bytes,
-                        int32_t* sorted_in_alt_host, void* stream);
+/* S4c.  Stable multisplit of the depth-ordered stream into the leaves' lists: inst_gid[leaf.inst_begin ..
+ * + leaf.inst_count) = Gaussian ids overlapping the leaf, nearest first.  Three kernels (count, scan, scatter) over
+ * chunks of C = g2pc_multisplit_chunk(leaf_cap) sorted entries; matrix: ceil(n / C) x leaves uint32 scratch.
+ * leaf_cap = max_leaves given to g2pc_build_tree. */
+int32_t g2pc_multisplit_chunk(int32_t leaf_cap);
+int g2pc_multisplit(const uint64_t* val_sorted, int64_t n, const void* proj, int32_t width, int32_t height,
+                    const int32_t* tables, int32_t num_levels, uint32_t level_mask, const int32_t* node_leaf,
+                    const g2pc_leaf_t* leaves, const int32_t* header, int32_t leaf_cap, uint32_t* matrix,
+                    uint32_t* inst_gid, void* stream);
 
 /* S5.  Front-to-back blend of every leaf (gauss_render.py:337-369) + per-Gaussian maximum contribution / arg-max pixel
  * (:371-385) published as cam_best[g] = max((bits(contribution) << 32) | ~leaf_pixel_index).
- * max_leaf_pixels_quads: upper bound of ceil(w/4)*h over the leaves.  max_contrib (n) f32: the running maxima of the
- * earlier cameras (read-only here; contributions that cannot beat them skip the bookkeeping).  leaf_colour:
- * (total_pix,3) f32.
- * owner: uint32 per image pixel (zero-filled): 1 + index of the last leaf pixel covering it.
- * work_counter: one int32, zero-filled by the caller (persistent CTAs pull (leaf, slab) items, heaviest leaf first). */
-int g2pc_blend(const g2pc_leaf_t* leaves, const int32_t* leaf_order, int32_t num_leaves, int32_t max_leaf_pixels_quads,
-               const uint32_t* inst_gid, const void* proj, uint64_t* cam_best, const float* max_contrib,
-               float* leaf_colour, uint32_t* owner, int32_t width, int32_t height, float background,
-               int32_t* work_counter, void* stream);
+ * The leaf count comes from `header` (device).  max_leaf_pixels_quads: upper bound of ceil(w/4)*h over the leaves.
+ * max_contrib (n) f32: the running maxima of the earlier cameras (read-only here; contributions that cannot beat
+ * them skip the bookkeeping).  leaf_colour: (pix_capacity,3) f32.  owner: uint32 per image pixel (zero on entry):
+ * 1 + index of the last leaf pixel covering it.  work_counters: cleared by g2pc_build_tree (persistent CTAs pull
+ * (leaf, slab) items, heaviest leaf first).
+ * t_stop: a warp stops walking its leaf's list once ALL of its 128 pixels have transmittance T < t_stop; every
+ * contribution it skips is then < t_stop and their sum per pixel is < t_stop.  t_stop = 0 selects FLT_MIN (only
+ * contributions that underflow are dropped: the strict-parity setting); the reference's CUDA back-end stops each pixel
+ * at T < 1e-4 (forward.cu:415).  stats: G2PC_STAT_WORDS uint64 or NULL. */
+int g2pc_blend(const g2pc_leaf_t* leaves, const int32_t* leaf_order, const int32_t* header,
+               int32_t max_leaf_pixels_quads, const uint32_t* inst_gid, const void* proj, uint64_t* cam_best,
+               const float* max_contrib, float* leaf_colour, uint32_t* owner, int32_t width, int32_t height,
+               float background, float t_stop, int32_t* work_counters, uint64_t* stats, void* stream);
 
 /* S6.  Fold one camera into the per-Gaussian accumulators (gauss_render.py:387-395; the role of
  * GaussianRasterizer.update_max_contributions, gaussian_pointcloud_rasterization/__init__.py:142-152):
  * where the camera's best contribution beats max_contrib[g] (strict >) store it and the blended colour of the winning
- * pixel.  Clears cam_best. */
+ * pixel.  Clears cam_best.  first_frame (n) int32 or NULL: set to `frame` where the maximum was raised (the multi-GPU
+ * merge needs the index of the camera that first reached each maximum, g2pc/dist.py). */
 int g2pc_accumulate(uint64_t* cam_best, const float* leaf_colour, int64_t n, float* max_contrib, float* colours,
-                    void* stream);
+                    int32_t* first_frame, int32_t frame, void* stream);
 
 /* Rendered image (H,W,3) f32, flipped left-right like the reference (gauss_render.py:402); clears `owner`. */
 int g2pc_compose_image(uint32_t* owner, const float* leaf_colour, int32_t width, int32_t height, float background,

@@ -21,7 +21,21 @@ import types
 import numpy as np
 import torch
 
-REF_ROOT = os.environ.get("G2PC_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# staged byte-for-byte copy of the reference's Python modules (baseline/build_ref.py; git-ignored, travels to the GPU box)
+STAGED_ROOT = os.path.join(os.path.dirname(_HERE), "baseline", "_ref", "py")
+STAGED_EXT_ROOT = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")
+
+
+def _find_root():
+    env = os.environ.get("G2PC_REFERENCE_ROOT")
+    for cand in ([env] if env else []) + ["/root/reference", STAGED_ROOT]:
+        if cand and os.path.isfile(os.path.join(cand, "gauss_to_pc.py")):
+            return cand
+    return env or "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 _FACTORIES = ["zeros", "ones", "full", "eye", "tensor", "arange", "empty", "zeros_like", "ones_like", "full_like",
               "empty_like", "linspace", "rand", "randn", "as_tensor"]
@@ -117,6 +131,10 @@ def load():
              "mask_dataloader", "gauss_to_pc"]
     saved_mods = {n: sys.modules.pop(n) for n in names if n in sys.modules}
     sys.path.insert(0, REF_ROOT)
+    # the reference's CUDA extension package (gauss_render.py:470 imports it lazily) — only present when built
+    ext_on_path = os.path.isdir(os.path.join(STAGED_EXT_ROOT, "gaussian_pointcloud_rasterization"))
+    if ext_on_path and STAGED_EXT_ROOT not in sys.path:
+        sys.path.append(STAGED_EXT_ROOT)
     try:
         mods = {n: importlib.import_module(n) for n in names}
     finally:

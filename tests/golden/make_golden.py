@@ -84,8 +84,22 @@ def make_colour(name, n, scene_seed, ncams, res):
     print(name, "images", np.stack(imgs).shape, "seen", int((R.gaussian_max_contribution > 0).sum()))
 
 
+def make_sh(name="sh_a", n=400, seed=1320):
+    """eval_sh of the reference (gauss_render.py:43-99), degrees 0..3, on seeded coefficients / unit directions; the
+    rendered colour is eval_sh + 0.5 clamped at 0 (forward.cu:65-72)."""
+    ref = ref_shim.load()
+    g = torch.Generator().manual_seed(seed)
+    sh = (0.4 * torch.randn(n, 3, 16, generator=g)).float()
+    d = torch.randn(n, 3, generator=g)
+    d = (d / d.norm(dim=1, keepdim=True)).float()
+    out = {f"deg{deg}": ref.gauss_render.eval_sh(deg, sh[..., : (deg + 1) ** 2], d).numpy() for deg in range(4)}
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=np.array([n, seed], dtype=np.int64), **out)
+    print(name, {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    make_sh()
     for name, args in SAMPLING_CASES.items():
         make_sampling(name, *args)
     for name, args in COLOUR_CASES.items():

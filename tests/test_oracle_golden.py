@@ -69,6 +69,29 @@ def test_colour_oracle_matches_reference_golden(name):
         assert np.array_equal(O.gaussian_max_contribution > 0.05, g["visible"]), "visibility mask must be exact"
 
 
+def _sh_inputs(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    sh = (0.4 * torch.randn(n, 3, 16, generator=g)).float()
+    d = torch.randn(n, 3, generator=g)
+    return sh, (d / d.norm(dim=1, keepdim=True)).float()
+
+
+def test_sh_colour_matches_reference_eval_sh():
+    """oracle.render.sh_colour == clamp(eval_sh + 0.5, 0) of the reference (gauss_render.py:43-99), degrees 0-3:
+    against the committed golden (outputs of the unmodified eval_sh) and, in the build container, the live function."""
+    from oracle import ref_shim, render as orr
+    g = np.load(os.path.join(GOLDEN, "sh_a.npz"))
+    n, seed = [int(v) for v in g["meta"]]
+    sh, d = _sh_inputs(n, seed)
+    for deg in range(4):
+        want = np.maximum(g[f"deg{deg}"] + np.float32(0.5), 0)
+        got = orr.sh_colour(deg, sh[..., : (deg + 1) ** 2], d).numpy()
+        assert np.abs(got - want).max() <= 2.4e-7, f"deg {deg}"  # same polynomial, fp32 association only
+        if ref_shim.available():
+            live = ref_shim.load().gauss_render.eval_sh(deg, sh[..., : (deg + 1) ** 2], d).numpy()
+            assert np.array_equal(live, g[f"deg{deg}"]), "golden is stale"
+
+
 def test_philox_known_answers():
     """Random123 known-answer vectors for Philox4x32-10."""
     from oracle.philox import philox4x32_10

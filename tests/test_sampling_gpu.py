@@ -61,6 +61,11 @@ def test_cov_normals_magnitudes(lib):
     (3000, 200000, False, 5, 1),   # large k: multi-lane Gaussians
     (5000, 50000, False, 5, 0),    # |eps| <= std mode
     (300, 1000, False, 5, 1),
+    # BASELINE config C1 exactly (10 k Gaussians / 100 k points), both accept tests, exact and non-exact
+    (10000, 100000, False, 5, 1),
+    (10000, 100000, True, 100, 1),
+    (10000, 100000, False, 5, 0),
+    (10000, 100000, True, 100, 0),
 ])
 def test_generate_pointcloud_parity(lib, n, num_points, exact, attempts, cull_mode):
     import gauss_to_pc as g2p
@@ -137,6 +142,42 @@ def test_generate_pointcloud_parity(lib, n, num_points, exact, attempts, cull_mo
         assert float((pts[:upto] - o["points"][:upto]).abs().max()) < 1e-5
     print(f"[parity] n={n} P={num_points} exact={exact} cull={cull_mode}: emitted {t}, "
           f"mismatching Gaussians {n_mismatch}/{total_gauss}")
+
+
+@pytest.mark.parametrize("n,num_points", [(10000, 100000), (5000, 50000), (3000, 2000), (2000, 3_000_000)])
+def test_distribute_points_matches_oracle(lib, n, num_points):
+    """The PRODUCT's distribute_points (gauss_to_pc.py:73-90 restated on the GPU) against the oracle, bit-exactly,
+    on the same float64 magnitudes — including the zero -> one fix-up (num_points < n) and a large budget."""
+    import gauss_to_pc as g2p
+    from oracle import sampling as osamp
+    sc, cov0, cov, nrm, mags = _oracle_inputs(n, 1239)
+    want = osamp.distribute_points(mags, num_points)
+    got = g2p.distribute_points(mags.to(DEV), num_points).cpu()
+    assert got.dtype == want.dtype
+    assert torch.equal(got, want), f"{int((got != want).sum())} of {n} point counts differ"
+
+
+def test_small_std_exact_num_points_replays_instead_of_raising(lib):
+    """--mahalanobis_distance_std 0.5 with --exact_num_points needs far more than the first stored attempts
+    (acceptance ~3%); the sampler replays the deterministic stream with every attempt stored, like the reference
+    completes.  Counts against the oracle with the kernel's eps."""
+    import gauss_to_pc as g2p
+    from g2pc import config, sampler
+    from oracle import sampling as osamp
+    sc, cov0, cov, nrm, mags = _oracle_inputs(400, 1242)
+    d = scene_to(sc, DEV)
+    colours = sc["colours"] * 255
+    ppg = osamp.distribute_points(mags, 4000).to(torch.int32)
+    pts, cols, nr, total, status, dbg = g2p.sample_points_per_gaussian(
+        d["xyz"], cov.to(DEV), colours.to(DEV), nrm.to(DEV), ppg.to(DEV), 0.5, True, 100, SEED, 11)
+    assert dbg["plan"].attempts_stored == 100 > config.ATTEMPTS_STORED_FIRST
+    assert status.tolist()[0] == 0
+    t = int(total.item())
+    eps_fn = lambda gids, k, a: sampler.dump_eps(torch.as_tensor(gids, device=DEV), k, a, SEED, 11).cpu().numpy()
+    o = osamp.generate_pointcloud(sc["xyz"], cov, colours, nrm, mags, 4000, std=0.5, exact_num_points=True,
+                                  num_sample_attempts=100, eps_fn=eps_fn, ppg=ppg)
+    assert abs(t - o["points"].shape[0]) <= 4
+    assert torch.isfinite(pts[:t]).all()
 
 
 def test_emitted_points_obey_first_m_rule(lib):
