@@ -76,6 +76,21 @@ __device__ __forceinline__ void axis_range(const int32_t* __restrict__ s, const 
     hi = a;
 }
 
+// same query, started from a guess of the answer (lo_guess / hi_guess within a node or two of the exact bounds)
+__device__ __forceinline__ void axis_range_from(const int32_t* __restrict__ s, const int32_t* __restrict__ e, int level,
+                                                float rmin, float rmax, int lo_guess, int hi_guess, int& lo, int& hi) {
+    const int n = 1 << level;
+    if (!(rmax > rmin)) { lo = 1; hi = 0; return; }
+    int a = min(n - 1, max(0, lo_guess));
+    while (a < n && !((float)e[a] > rmin)) ++a;
+    while (a > 0 && (float)e[a - 1] > rmin) --a;
+    lo = a;
+    a = min(n - 1, max(0, hi_guess));
+    while (a >= 0 && !((float)s[a] < rmax)) --a;
+    while (a + 1 < n && (float)s[a + 1] < rmax) ++a;
+    hi = a;
+}
+
 __device__ __forceinline__ bool axis_member(const int32_t* __restrict__ s, const int32_t* __restrict__ e,
                                             const int32_t* __restrict__ f, int i) {
     return !(f[i] & QT_FLAG_DROPPED) && e[i] > s[i];

@@ -11,9 +11,9 @@
 // (g2pc_pack_geometry: 3 x float4 per Gaussian = xyz, Sigma as 6 floats, log2(opacity); three 16-byte loads per thread,
 // a warp reads 1536 contiguous bytes) and the SH rows (16-byte loads).  Membership is evaluated by range queries on the
 // per-level interval tables (g2pc/quadtree.py) instead of testing every tile against every Gaussian, and only on the
-// CANDIDATE levels (levels that have nodes small enough to be leaves): a node that is larger than max_tile_size splits
-// whatever its count, so its count is never needed.  The per-node overlap counts are accumulated in a shared-memory
-// histogram and flushed once per CTA.  The node range at the first candidate level is packed into the high word of
+// tables (g2pc/quadtree.py).  Exact overlap counts are taken on the CANDIDATE levels only (levels that have nodes small
+// enough to be leaves); above them every node splits by its size and only a non-empty flag is raised (plain stores, found
+// by walking up from the base range).  Counts and flags live in a shared-memory array flushed once per CTA.  The node range at the first candidate level is packed into the high word of
 // `val` (low word = Gaussian id): after the depth sort the multisplit kernels (s4_tree.cu) read their ranges from the
 // sorted stream and never gather.
 #include "colour_common.cuh"
@@ -187,24 +187,47 @@ __global__ void __launch_bounds__(256, 4) preprocess_kernel(const PreParams p) {
         float x0, x1, y0, y1;
         gaussian_rect(mx, my, radius, p.cam.width, p.cam.height, x0, x1, y0, y1);
         const float isx0 = 1.0f / (float)p.cam.width, isy0 = 1.0f / (float)p.cam.height;
+        // candidate levels (nodes small enough to be leaves): exact counts, first level -> packed range
+        int bxlo = 1, bxhi = 0, bylo = 1, byhi = 0;
         for (int l = p.base_level; l < p.meta.num_levels; ++l) {
-            if (!((p.level_mask >> l) & 1u)) continue;  // every node of this level splits by its size: counts unused
+            if (!((p.level_mask >> l) & 1u)) continue;
             const int o1 = (1 << l) - 1;
             int xlo, xhi, ylo, yhi;
             axis_range(T.xs + o1, T.xe + o1, l, x0, x1, isx0 * (float)(1 << l), xlo, xhi);
             if (xlo > xhi) continue;
             axis_range(T.ys + o1, T.ye + o1, l, y0, y1, isy0 * (float)(1 << l), ylo, yhi);
             if (ylo > yhi) continue;
-            if (l == p.base_level) range = g2pc_pack_range(xlo, xhi, ylo, yhi);
+            if (l == p.base_level) { range = g2pc_pack_range(xlo, xhi, ylo, yhi); bxlo = xlo; bxhi = xhi; bylo = ylo; byhi = yhi; }
             uint32_t* cnt = p.node_cnt + off2(l);
             for (int iy = ylo; iy <= yhi; ++iy) {
                 if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy)) continue;
-                const int fy = T.yf[o1 + iy];
                 for (int ix = xlo; ix <= xhi; ++ix) {
                     if (!axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) continue;
-                    if ((fy | T.xf[o1 + ix]) & QT_FLAG_BIG) continue;  // splits whatever its count
-                    if (use_hist) atomicAdd(s_hist + (off2(l) - p.hist_off) + (iy << l) + ix, 1u);
+                    if (use_hist) atomicAdd(s_hist + off2(l) + (iy << l) + ix, 1u);
                     else atomicAdd(cnt + (iy << l) + ix, 1u);
+                }
+            }
+        }
+        // levels above: every node splits by its size, only "is anything in it" matters (an empty tile is background
+        // and has no children, gauss_render.py:313-315).  A child tile may overhang its parent by a pixel, so this is
+        // NOT implied by the leaf-level counts: walk up from the base range (the exact range at level l starts within
+        // one node of the halved range of level l + 1) and raise plain flags — no atomics.
+        if (bxlo <= bxhi) {
+            int gxlo = bxlo, gxhi = bxhi, gylo = bylo, gyhi = byhi;
+            for (int l = p.base_level - 1; l >= 0; --l) {
+                const int o1 = (1 << l) - 1;
+                int xlo, xhi, ylo, yhi;
+                axis_range_from(T.xs + o1, T.xe + o1, l, x0, x1, gxlo >> 1, gxhi >> 1, xlo, xhi);
+                axis_range_from(T.ys + o1, T.ye + o1, l, y0, y1, gylo >> 1, gyhi >> 1, ylo, yhi);
+                gxlo = xlo; gxhi = xhi; gylo = ylo; gyhi = yhi;
+                if (xlo > xhi || ylo > yhi) continue;
+                for (int iy = ylo; iy <= yhi; ++iy) {
+                    if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy)) continue;
+                    for (int ix = xlo; ix <= xhi; ++ix) {
+                        if (!axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) continue;
+                        if (use_hist) s_hist[off2(l) + (iy << l) + ix] = 1u;
+                        else p.node_cnt[off2(l) + (iy << l) + ix] = 1u;
+                    }
                 }
             }
         }
@@ -218,7 +241,7 @@ __global__ void __launch_bounds__(256, 4) preprocess_kernel(const PreParams p) {
         __syncthreads();
         for (int k = threadIdx.x; k < p.nodes_2d; k += blockDim.x) {
             const uint32_t v = s_hist[k];
-            if (v) atomicAdd(p.node_cnt + p.hist_off + k, v);
+            if (v) atomicAdd(p.node_cnt + k, v);
         }
     }
 }
@@ -282,9 +305,8 @@ extern "C" int g2pc_preprocess(const void* geom, const float* colours, const flo
     p.base_level = __builtin_ctz(level_mask);
     G2PC_CHECK_ARG(p.base_level <= G2PC_RANGE_MAX_LEVEL, "first leaf-candidate level too deep for the packed node range");
     const int nodes_all = ((1 << (2 * num_levels)) - 1) / 3;
-    p.hist_off = ((1 << (2 * p.base_level)) - 1) / 3;
-    const int nodes_hist = nodes_all - p.hist_off;       // candidate levels only
-    p.nodes_2d = nodes_hist <= 24 * 1024 ? nodes_hist : 0;  // histogram in shared memory when it fits (<= 96 KB)
+    p.hist_off = 0;
+    p.nodes_2d = nodes_all <= 24 * 1024 ? nodes_all : 0;  // histogram in shared memory when it fits (<= 96 KB)
     const size_t smem = (size_t)6 * p.n1 * sizeof(int32_t) + (size_t)p.nodes_2d * sizeof(uint32_t);
     if (smem > 48 * 1024)
         G2PC_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -120,10 +120,11 @@ __global__ void __launch_bounds__(TB) tree_kernel(const TreeParams p) {
                     const int fx = p.tab.xf[o1 + ix], fy = p.tab.yf[o1 + iy];
                     if (!((fx | fy) & QT_FLAG_DROPPED)) {
                         cnt = p.node_cnt[node];
-                        // a node larger than max_tile_size splits whatever it holds (its count is not even collected):
-                        // if it is empty so are its descendants, and the same leaves come out (gauss_render.py:313-335)
+                        // cnt: exact on the leaf-candidate levels, a non-empty flag above them (a node larger than
+                        // max_tile_size splits whatever it holds — unless it is empty: then it is background and has
+                        // no children, gauss_render.py:313-335)
                         const bool big = ((fx | fy) & QT_FLAG_BIG) != 0;
-                        if (!big && cnt == 0) st = NODE_EMPTY;
+                        if (cnt == 0) st = NODE_EMPTY;
                         else if (big || cnt > (uint32_t)p.meta.max_gaussians_per_tile) {
                             st = NODE_SPLIT;
                             nl = -2;
@@ -263,6 +264,14 @@ __device__ __forceinline__ void for_each_leaf(const MsParams& p, const QtTables&
     const int lb = p.base_level;
     const int o1 = (1 << lb) - 1;
     bool deeper = false;
+    if (p.meta.num_levels > lb + 1) {
+        // a child tile may overhang its parent by a pixel to the right / below (children are ceil(size / 2) wide): a
+        // Gaussian can sit in a deeper leaf of the base node just left of / above its own base range
+        const int ex = max(xlo - 1, 0), ey = max(ylo - 1, 0);
+        for (int iy = ey; iy <= yhi; ++iy)
+            for (int ix = ex; ix <= xhi; ++ix)
+                if ((iy < ylo || ix < xlo) && s_leaf[(iy << lb) + ix] == -2) deeper = true;
+    }
     for (int iy = ylo; iy <= yhi; ++iy) {
         if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy)) continue;
         for (int ix = xlo; ix <= xhi; ++ix) {

@@ -261,6 +261,7 @@ class GaussPythonRenderer():
             self._poll(block_if_more_than=8)
         if not self.compose_image:
             return None, None, None, None
+        t = self._last_tables  # (a replay may have switched to a deeper table set)
         # confirmed frames get their own tensor, like the reference; in async mode the shared buffer is handed out (it is
         # final once flush() has run and is overwritten by the next camera)
         return (t["image"] if self.async_mode else t["image"].clone()), None, None, None

@@ -217,7 +217,7 @@ def sample_points_per_gaussian(xyz, covariances, colours, normals, points_per_ga
     n_used = int(sum(c for (_, _, _, c) in bins))
     perm = order[:n_used].to(torch.int32)
     global LAST_SAMPLE_STATS
-    LAST_SAMPLE_STATS = {"n_active": n_used, "bins": len(bins)}
+    LAST_SAMPLE_STATS = {"n_active": n_used, "bins": len(bins), "n_gaussians": int(xyz.shape[0])}
 
     for A in _attempt_ladder(num_sample_attempts):
         plan = sampler.SamplePlan([(n - 1, count) for (_, _, n, count) in bins], A, include_centres=True)
