@@ -81,10 +81,10 @@ def get_camera(renderer_type, transform, cam_intrinsic, colour_resolution=None, 
         if tuple(mask.shape[:2]) != (native_h, native_w):
             raise Exception("Size of mask must match size of input image")
         mask = mask.flatten()
+    if renderer_type == "cuda":
+        return _cuda_settings(transform, int(native_w * scale), int(native_h * scale), float(cam_intrinsic[2]) * scale,
+                              float(cam_intrinsic[3]) * scale, sh_degree, white_bkgd, mask)
     if renderer_type != "python":
-        if renderer_type == "cuda":
-            raise NotImplementedError("renderer_type='cuda' cameras (z-forward convention, GaussianRasterizationSettings) "
-                                      "belong to the not-yet-built 16x16-tile back-end; use renderer_type='python'")
         raise Exception(f"Renderer of type {renderer_type} is not supported")
     cam = Camera(int(native_w * scale), int(native_h * scale), float(cam_intrinsic[2]) * scale,
                  float(cam_intrinsic[3]) * scale, transform)
@@ -92,3 +92,35 @@ def get_camera(renderer_type, transform, cam_intrinsic, colour_resolution=None, 
     cam.white_bkgd = white_bkgd
     cam.mask = mask
     return cam
+
+
+def _cuda_settings(transform, img_width, img_height, focal_x, focal_y, sh_degree, white_bkgd, mask):
+    """GaussianRasterizationSettings of the CUDA back-end (camera_handler.py:72-108): the OpenGL c2w is turned into a
+    z-forward camera by negating columns 1:3 (the reference does that IN PLACE on the caller's tensor, :75; a copy is
+    flipped here), viewmatrix = inv(c2w)^T, projmatrix = viewmatrix @ projection^T, znear 10 / zfar 100, debug=True,
+    antialiasing=False.  The 4x4 algebra runs on the host in float32; the settings carry host copies of the matrices
+    (the kernels take them by value) next to the tensor fields of the reference."""
+    from g2pc.rasterizer import GaussianRasterizationSettings
+
+    class Settings(GaussianRasterizationSettings):
+        pass
+
+    dev = transform.device if torch.is_tensor(transform) else torch.device("cpu")
+    c2w = torch.as_tensor(transform).detach().to("cpu", torch.float32).clone()
+    c2w[:, 1:3] = -c2w[:, 1:3]
+    fovX, fovY = focal2fov(focal_x, img_width), focal2fov(focal_y, img_height)
+    proj = getProjectionMatrix(znear=10, zfar=100, fovX=fovX, fovY=fovY).transpose(0, 1)
+    view = torch.linalg.inv(c2w).permute(1, 0).contiguous()
+    campos = view.inverse()[3, :3].contiguous()
+    full = (view @ proj).contiguous()
+    bg = [1.0, 1.0, 1.0] if white_bkgd else [0.0, 0.0, 0.0]
+    on_dev = (lambda t: t.to(dev)) if dev.type == "cuda" else (lambda t: t)
+    s = Settings(image_height=int(img_height), image_width=int(img_width), tanfovx=math.tan(fovX * 0.5),
+                 tanfovy=math.tan(fovY * 0.5), bg=on_dev(torch.tensor(bg)), scale_modifier=1.0, viewmatrix=on_dev(view),
+                 projmatrix=on_dev(full), sh_degree=sh_degree, campos=on_dev(campos), mask=mask, prefiltered=False,
+                 debug=True, antialiasing=False)
+    s._viewmatrix_host = view.reshape(-1).tolist()
+    s._projmatrix_host = full.reshape(-1).tolist()
+    s._campos_host = campos.tolist()
+    s._bg_host = bg
+    return s

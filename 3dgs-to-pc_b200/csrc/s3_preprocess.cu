@@ -100,18 +100,21 @@ __global__ void __launch_bounds__(256, 4) preprocess_kernel(const PreParams p) {
     const int64_t cta_base = (int64_t)blockIdx.x * PRE_PER_CTA;
   for (int it = 0; it < PRE_PER_CTA / 256; ++it) {
     const int64_t i = cta_base + it * 256 + threadIdx.x;
-    if (i >= p.n) break;
+    if (cta_base + it * 256 >= p.n) break;  // uniform: the whole CTA is past the end
+    const int64_t il = i < p.n ? i : p.n - 1;  // lanes past the end shadow the last Gaussian and write nothing
 
     const float* V = p.cam.view;
     const float* P = p.cam.proj;
-    const float4 g0 = __ldg(p.geom + 3 * i), g1 = __ldg(p.geom + 3 * i + 1), g2 = __ldg(p.geom + 3 * i + 2);
+    const float4 g0 = __ldg(p.geom + 3 * il), g1 = __ldg(p.geom + 3 * il + 1), g2 = __ldg(p.geom + 3 * il + 2);
     const float m0 = g0.x, m1 = g0.y, m2 = g0.z;
 
     // p_view = [mu, 1] @ V   (row-vector convention)
     float pv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) pv[j] = fmaf(m2, V[8 + j], fmaf(m1, V[4 + j], fmaf(m0, V[j], V[12 + j])));
-    const bool in_front = pv[2] <= -0.000001f;
+    const bool in_front = (pv[2] <= -0.000001f) && (i < p.n);
+    bool has_rect = false;
+    float x0 = 0.f, x1 = 0.f, y0 = 0.f, y1 = 0.f;
 
     float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0;
     uint32_t range = G2PC_RANGE_EMPTY;
@@ -173,23 +176,41 @@ __global__ void __launch_bounds__(256, 4) preprocess_kernel(const PreParams p) {
         if (p.shs) {
             const float dx = m0 - p.cam.campos[0], dy = m1 - p.cam.campos[1], dz = m2 - p.cam.campos[2];
             const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-            rgb = sh_to_rgb(p.shs + (int64_t)i * 3 * p.sh_stride, p.sh_stride, p.sh_degree,
+            rgb = sh_to_rgb(p.shs + (int64_t)il * 3 * p.sh_stride, p.sh_stride, p.sh_degree,
                             make_float3(dx * inv, dy * inv, dz * inv));
         } else {
-            rgb = make_float3(p.colours[3 * i], p.colours[3 * i + 1], p.colours[3 * i + 2]);
+            rgb = make_float3(p.colours[3 * il], p.colours[3 * il + 1], p.colours[3 * il + 2]);
         }
         q0 = make_float4(mx, my, k00 * K, (k01 + k10) * K);
         // alpha = min(0.99, opacity * exp(power)) = min(0.99, exp2(power' + log2(opacity)))
         q1 = make_float4(k11 * K, g2.y, rgb.x, rgb.y);
         q2 = make_float4(rgb.z, pv[2], radius, 1.0f);
 
-        // ---- quadtree membership: flags for nodes that split anyway, exact counts for leaf candidates ----
-        float x0, x1, y0, y1;
         gaussian_rect(mx, my, radius, p.cam.width, p.cam.height, x0, x1, y0, y1);
-        const float isx0 = 1.0f / (float)p.cam.width, isy0 = 1.0f / (float)p.cam.height;
-        // candidate levels (nodes small enough to be leaves): exact counts, first level -> packed range
-        int bxlo = 1, bxhi = 0, bylo = 1, byhi = 0;
-        for (int l = p.base_level; l < p.meta.num_levels; ++l) {
+        has_rect = true;
+    }
+    // ---- quadtree membership (all 32 lanes: the base-level walk is warp-cooperative) ----------------------------------
+    const float isx0 = 1.0f / (float)p.cam.width, isy0 = 1.0f / (float)p.cam.height;
+    int bxlo = 1, bxhi = 0, bylo = 1, byhi = 0;
+    {
+        const int l = p.base_level;
+        const int o1 = (1 << l) - 1;
+        if (has_rect) {
+            axis_range(T.xs + o1, T.xe + o1, l, x0, x1, isx0 * (float)(1 << l), bxlo, bxhi);
+            axis_range(T.ys + o1, T.ye + o1, l, y0, y1, isy0 * (float)(1 << l), bylo, byhi);
+            if (bxlo > bxhi || bylo > byhi) { bxlo = 1; bxhi = 0; bylo = 1; byhi = 0; }
+            else range = g2pc_pack_range(bxlo, bxhi, bylo, byhi);
+        }
+        uint32_t* cnt = p.node_cnt + off2(l);
+        warp_for_each_node(bxlo, bxhi, bylo, byhi, 0u, [&](int ix, int iy, int, uint32_t) {
+            if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy) || !axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) return;
+            if (use_hist) atomicAdd(s_hist + off2(l) + (iy << l) + ix, 1u);
+            else atomicAdd(cnt + (iy << l) + ix, 1u);
+        });
+    }
+    if (has_rect && bxlo <= bxhi) {
+        // deeper candidate levels exist only after a count-driven split asked for them (rare): per lane
+        for (int l = p.base_level + 1; l < p.meta.num_levels; ++l) {
             if (!((p.level_mask >> l) & 1u)) continue;
             const int o1 = (1 << l) - 1;
             int xlo, xhi, ylo, yhi;
@@ -197,7 +218,6 @@ __global__ void __launch_bounds__(256, 4) preprocess_kernel(const PreParams p) {
             if (xlo > xhi) continue;
             axis_range(T.ys + o1, T.ye + o1, l, y0, y1, isy0 * (float)(1 << l), ylo, yhi);
             if (ylo > yhi) continue;
-            if (l == p.base_level) { range = g2pc_pack_range(xlo, xhi, ylo, yhi); bxlo = xlo; bxhi = xhi; bylo = ylo; byhi = yhi; }
             uint32_t* cnt = p.node_cnt + off2(l);
             for (int iy = ylo; iy <= yhi; ++iy) {
                 if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy)) continue;
@@ -212,30 +232,30 @@ __global__ void __launch_bounds__(256, 4) preprocess_kernel(const PreParams p) {
         // and has no children, gauss_render.py:313-315).  A child tile may overhang its parent by a pixel, so this is
         // NOT implied by the leaf-level counts: walk up from the base range (the exact range at level l starts within
         // one node of the halved range of level l + 1) and raise plain flags — no atomics.
-        if (bxlo <= bxhi) {
-            int gxlo = bxlo, gxhi = bxhi, gylo = bylo, gyhi = byhi;
-            for (int l = p.base_level - 1; l >= 0; --l) {
-                const int o1 = (1 << l) - 1;
-                int xlo, xhi, ylo, yhi;
-                axis_range_from(T.xs + o1, T.xe + o1, l, x0, x1, gxlo >> 1, gxhi >> 1, xlo, xhi);
-                axis_range_from(T.ys + o1, T.ye + o1, l, y0, y1, gylo >> 1, gyhi >> 1, ylo, yhi);
-                gxlo = xlo; gxhi = xhi; gylo = ylo; gyhi = yhi;
-                if (xlo > xhi || ylo > yhi) continue;
-                for (int iy = ylo; iy <= yhi; ++iy) {
-                    if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy)) continue;
-                    for (int ix = xlo; ix <= xhi; ++ix) {
-                        if (!axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) continue;
-                        if (use_hist) s_hist[off2(l) + (iy << l) + ix] = 1u;
-                        else p.node_cnt[off2(l) + (iy << l) + ix] = 1u;
-                    }
+        int gxlo = bxlo, gxhi = bxhi, gylo = bylo, gyhi = byhi;
+        for (int l = p.base_level - 1; l >= 0; --l) {
+            const int o1 = (1 << l) - 1;
+            int xlo, xhi, ylo, yhi;
+            axis_range_from(T.xs + o1, T.xe + o1, l, x0, x1, gxlo >> 1, gxhi >> 1, xlo, xhi);
+            axis_range_from(T.ys + o1, T.ye + o1, l, y0, y1, gylo >> 1, gyhi >> 1, ylo, yhi);
+            gxlo = xlo; gxhi = xhi; gylo = ylo; gyhi = yhi;
+            if (xlo > xhi || ylo > yhi) continue;
+            for (int iy = ylo; iy <= yhi; ++iy) {
+                if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy)) continue;
+                for (int ix = xlo; ix <= xhi; ++ix) {
+                    if (!axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) continue;
+                    if (use_hist) s_hist[off2(l) + (iy << l) + ix] = 1u;
+                    else p.node_cnt[off2(l) + (iy << l) + ix] = 1u;
                 }
             }
         }
     }
+    if (i < p.n) {
     float4* rec = p.proj + 3 * i;
     rec[0] = q0; rec[1] = q1; rec[2] = q2;
     p.depth_key[i] = in_front ? __float_as_uint(-pv[2]) : 0xFFFFFFFFu;
     p.val[i] = ((unsigned long long)range << 32) | (unsigned long long)(uint32_t)i;
+    }
   }
     if (use_hist) {
         __syncthreads();

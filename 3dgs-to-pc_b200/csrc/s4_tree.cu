@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(TB) tree_kernel(const TreeParams p) {
     if (threadIdx.x == 0) {
         const int cap_over = (inst_total > p.inst_capacity || (long long)pix_base > p.pix_capacity ||
                               (long long)p.ms_chunks * (long long)nl > p.matrix_capacity || inst_total > 0x7FFFFFFFll)
+                             // (ms_chunks = rows the multisplit needs: chunks + segments, g2pc_multisplit_rows)
                                  ? 1 : 0;
         p.header[G2PC_HDR_NUM_LEAVES] = leaf_base;
         p.header[G2PC_HDR_TOTAL_INST] = (int32_t)(inst_total & 0xFFFFFFFFll);
@@ -253,35 +254,45 @@ struct MsParams {
     uint32_t* matrix;      // [chunk][num_leaves]: counts, then absolute list offsets (in place)
     uint32_t* inst_gid;
     int32_t leaf_cap;      // leaves the shared-memory tables are sized for (<= max_leaves of the tree)
+    int32_t grid_w;        // > 0: flat tile grid (s7_tiles.cu): leaf = iy * grid_w + ix, the packed range is the tile rect
 };
 
+// f(leaf, owner_lane, owner_gid) for every leaf the lane's entry overlaps; warp-cooperative (all 32 lanes must call).
 template <typename F>
 __device__ __forceinline__ void for_each_leaf(const MsParams& p, const QtTables& T, const int32_t* __restrict__ s_leaf,
                                               uint32_t range, uint32_t gid, F f) {
     int xlo, xhi, ylo, yhi;
     g2pc_unpack_range(range, xlo, xhi, ylo, yhi);
-    if (xlo > xhi) return;
+    if (p.grid_w > 0) {
+        warp_for_each_node(xlo, xhi, ylo, yhi, gid,
+                           [&](int ix, int iy, int owner, uint32_t og) { f(iy * p.grid_w + ix, owner, og); });
+        return;
+    }
     const int lb = p.base_level;
     const int o1 = (1 << lb) - 1;
-    bool deeper = false;
-    if (p.meta.num_levels > lb + 1) {
+    unsigned deeper = 0;
+    warp_for_each_node(xlo, xhi, ylo, yhi, gid, [&](int ix, int iy, int owner, uint32_t og) {
+        if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy) || !axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) return;
+        const int32_t v = s_leaf[(iy << lb) + ix];
+        if (v >= 0) f(v, owner, og);
+        else if (v == -2) deeper |= 1u << owner;
+    });
+    if (p.meta.num_levels <= lb + 1) return;
+    // ---- count-driven splits below the base level (rare): per lane ----
+    // combine the flags raised on behalf of each owner
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) deeper |= __shfl_xor_sync(0xffffffffu, deeper, o);
+    const int lane = threadIdx.x & 31;
+    bool mine = (deeper >> lane) & 1u;
+    if (!mine && xlo <= xhi) {
         // a child tile may overhang its parent by a pixel to the right / below (children are ceil(size / 2) wide): a
         // Gaussian can sit in a deeper leaf of the base node just left of / above its own base range
         const int ex = max(xlo - 1, 0), ey = max(ylo - 1, 0);
         for (int iy = ey; iy <= yhi; ++iy)
             for (int ix = ex; ix <= xhi; ++ix)
-                if ((iy < ylo || ix < xlo) && s_leaf[(iy << lb) + ix] == -2) deeper = true;
+                if ((iy < ylo || ix < xlo) && s_leaf[(iy << lb) + ix] == -2) mine = true;
     }
-    for (int iy = ylo; iy <= yhi; ++iy) {
-        if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy)) continue;
-        for (int ix = xlo; ix <= xhi; ++ix) {
-            if (!axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) continue;
-            const int32_t v = s_leaf[(iy << lb) + ix];
-            if (v >= 0) f(v);
-            else if (v == -2) deeper = true;
-        }
-    }
-    if (!deeper || p.meta.num_levels <= lb + 1) return;
+    if (!mine) return;
     const float4 q0 = __ldg(p.proj + 3 * (int64_t)gid);
     const float4 q2 = __ldg(p.proj + 3 * (int64_t)gid + 2);
     float x0, x1, y0, y1;
@@ -301,7 +312,7 @@ __device__ __forceinline__ void for_each_leaf(const MsParams& p, const QtTables&
             for (int ix = axlo; ix <= axhi; ++ix) {
                 if (!axis_member(T.xs + ol, T.xe + ol, T.xf + ol, ix)) continue;
                 const int32_t v = __ldg(nl + (iy << l) + ix);
-                if (v >= 0) f(v);
+                if (v >= 0) f(v, lane, gid);
             }
         }
     }
@@ -309,6 +320,7 @@ __device__ __forceinline__ void for_each_leaf(const MsParams& p, const QtTables&
 
 // shared memory of the count / scatter kernels: [6 * n1 table ints][4^base node->leaf ints][payload]
 __device__ __forceinline__ int32_t* ms_load_common(const MsParams& p, int32_t* smem, QtTables& T) {
+    if (p.grid_w > 0) { T = p.tab; return smem; }  // tile grid: nothing to stage
     T = load_tables(p.tab, p.n1, smem);  // ends with __syncthreads()
     int32_t* s_leaf = smem + 6 * p.n1;
     const int nb = 1 << (2 * p.base_level);
@@ -317,40 +329,57 @@ __device__ __forceinline__ int32_t* ms_load_common(const MsParams& p, int32_t* s
     return s_leaf;
 }
 
+// CTA b owns the contiguous chunks [b * per_cta, (b + 1) * per_cta) ("segment" b).
+// count:   matrix[c][leaf] = instances of `leaf` in the chunks of the segment BEFORE c (running total in shared memory),
+//          aux[b][leaf] = instances of the whole segment;  scan: aux -> absolute list offset of the segment's first
+//          instance;  scatter: position = aux[b][leaf] + matrix[c][leaf] + rank inside the chunk.
 template <int C>
-__global__ void __launch_bounds__(C) ms_count_kernel(const MsParams p) {
+__global__ void __launch_bounds__(C) ms_count_kernel(const MsParams p, int32_t chunks, int32_t per_cta) {
     extern __shared__ int32_t smem_ms[];
     if (p.header[G2PC_HDR_POISON] != 0) return;
     const int nl = p.header[G2PC_HDR_NUM_LEAVES];
     QtTables T;
     int32_t* s_leaf = ms_load_common(p, smem_ms, T);
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_leaf + (1 << (2 * p.base_level)));
-    for (int i = threadIdx.x; i < nl; i += C) s_hist[i] = 0u;
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_leaf + (p.grid_w > 0 ? 0 : (1 << (2 * p.base_level))));  // this chunk
+    uint32_t* s_run = s_hist + p.leaf_cap;                                              // earlier chunks of the segment
+    for (int i = threadIdx.x; i < nl; i += C) { s_hist[i] = 0u; s_run[i] = 0u; }
     __syncthreads();
-    const int64_t k = (int64_t)blockIdx.x * C + threadIdx.x;
-    if (k < p.n) {
-        const unsigned long long v = p.val_sorted[k];
-        for_each_leaf(p, T, s_leaf, (uint32_t)(v >> 32), (uint32_t)v, [&](int leaf) { atomicAdd(s_hist + leaf, 1u); });
+    const int c0 = blockIdx.x * per_cta, c1 = min(chunks, c0 + per_cta);
+    for (int c = c0; c < c1; ++c) {
+        const int64_t k = (int64_t)c * C + threadIdx.x;
+        unsigned long long v = (unsigned long long)G2PC_RANGE_EMPTY << 32;
+        if (k < p.n) v = p.val_sorted[k];
+        for_each_leaf(p, T, s_leaf, (uint32_t)(v >> 32), (uint32_t)v,
+                      [&](int leaf, int, uint32_t) { atomicAdd(s_hist + leaf, 1u); });
+        __syncthreads();
+        uint32_t* row = p.matrix + (int64_t)c * nl;
+        for (int i = threadIdx.x; i < nl; i += C) {
+            const uint32_t h = s_hist[i], r = s_run[i];
+            row[i] = r;
+            s_run[i] = r + h;
+            s_hist[i] = 0u;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    uint32_t* row = p.matrix + (int64_t)blockIdx.x * nl;
-    for (int i = threadIdx.x; i < nl; i += C) row[i] = s_hist[i];
+    uint32_t* aux = p.matrix + (int64_t)chunks * nl + (int64_t)blockIdx.x * nl;
+    for (int i = threadIdx.x; i < nl; i += C) aux[i] = s_run[i];
 }
 
-// per leaf (column): counts -> absolute offsets of the chunk's instances inside inst_gid.  CTA = 32 leaves x 32 row
-// segments; the matrix is read twice (sum, then rewrite).
-__global__ void __launch_bounds__(1024) ms_scan_kernel(const MsParams p, int32_t chunks) {
+// per leaf (column) of `m` (rows x num_leaves): totals -> absolute offsets (exclusive prefix over the rows + the leaf's
+// list offset).  CTA = 32 leaves x 32 row groups; the matrix is read twice (sum, then rewrite).
+__global__ void __launch_bounds__(1024) ms_scan_kernel(const MsParams p, int32_t chunks, int32_t rows) {
     __shared__ uint32_t s_sum[32][33];
     if (p.header[G2PC_HDR_POISON] != 0) return;
     const int nl = p.header[G2PC_HDR_NUM_LEAVES];
+    uint32_t* __restrict__ m = p.matrix + (int64_t)chunks * nl;  // the segment totals written by the count kernel
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int seg = (chunks + 31) / 32;
+    const int seg = (rows + 31) / 32;
     for (int leaf0 = blockIdx.x * 32; leaf0 < nl; leaf0 += gridDim.x * 32) {
         const int leaf = leaf0 + tx;
-        const int r0 = ty * seg, r1 = min(chunks, r0 + seg);
+        const int r0 = min(rows, ty * seg), r1 = min(rows, r0 + seg);
         uint32_t sum = 0;
         if (leaf < nl)
-            for (int r = r0; r < r1; ++r) sum += p.matrix[(int64_t)r * nl + leaf];
+            for (int r = r0; r < r1; ++r) sum += m[(int64_t)r * nl + leaf];
         s_sum[ty][tx] = sum;
         __syncthreads();
         if (ty == 0) {
@@ -361,7 +390,7 @@ __global__ void __launch_bounds__(1024) ms_scan_kernel(const MsParams p, int32_t
         if (leaf < nl) {
             uint32_t run = s_sum[ty][tx];
             for (int r = r0; r < r1; ++r) {
-                uint32_t* c = p.matrix + (int64_t)r * nl + leaf;
+                uint32_t* c = m + (int64_t)r * nl + leaf;
                 const uint32_t t = *c;
                 *c = run;
                 run += t;
@@ -372,59 +401,76 @@ __global__ void __launch_bounds__(1024) ms_scan_kernel(const MsParams p, int32_t
 }
 
 template <int C>
-__global__ void __launch_bounds__(C) ms_scatter_kernel(const MsParams p) {
+__global__ void __launch_bounds__(C) ms_scatter_kernel(const MsParams p, int32_t chunks, int32_t per_cta) {
     extern __shared__ int32_t smem_ms[];
     if (p.header[G2PC_HDR_POISON] != 0) return;
     const int nl = p.header[G2PC_HDR_NUM_LEAVES];
     constexpr int WORDS = C / 32;
     QtTables T;
     int32_t* s_leaf = ms_load_common(p, smem_ms, T);
-    uint32_t* s_gid = reinterpret_cast<uint32_t*>(s_leaf + (1 << (2 * p.base_level)));
-    uint32_t* s_bits = s_gid + C;  // [WORDS][nl]
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_leaf + (p.grid_w > 0 ? 0 : (1 << (2 * p.base_level))));  // [WORDS][nl], zero between chunks
     for (int i = threadIdx.x; i < WORDS * nl; i += C) s_bits[i] = 0u;
     __syncthreads();
-    const int64_t k = (int64_t)blockIdx.x * C + threadIdx.x;
-    if (k < p.n) {
-        const unsigned long long v = p.val_sorted[k];
-        s_gid[threadIdx.x] = (uint32_t)v;
-        const uint32_t bit = 1u << (threadIdx.x & 31);
-        uint32_t* rowbits = s_bits + (threadIdx.x >> 5) * nl;
-        for_each_leaf(p, T, s_leaf, (uint32_t)(v >> 32), (uint32_t)v, [&](int leaf) { atomicOr(rowbits + leaf, bit); });
-    }
-    __syncthreads();
-    const uint32_t* row = p.matrix + (int64_t)blockIdx.x * nl;
-    for (int leaf = threadIdx.x; leaf < nl; leaf += C) {
-        uint32_t pos = row[leaf];
-#pragma unroll
-        for (int w = 0; w < WORDS; ++w) {
-            uint32_t word = s_bits[w * nl + leaf];
-            while (word) {
-                const int b = __ffs(word) - 1;
-                word &= word - 1u;
-                p.inst_gid[pos++] = s_gid[w * 32 + b];
-            }
-        }
+    const uint32_t* aux = p.matrix + (int64_t)chunks * nl + (int64_t)blockIdx.x * nl;
+    const int w = threadIdx.x >> 5;  // the warp = the 32-entry group of the chunk
+    uint32_t* mybits = s_bits + w * nl;
+    const int c0 = blockIdx.x * per_cta, c1 = min(chunks, c0 + per_cta);
+    for (int c = c0; c < c1; ++c) {
+        const int64_t k = (int64_t)c * C + threadIdx.x;
+        unsigned long long v = (unsigned long long)G2PC_RANGE_EMPTY << 32;
+        if (k < p.n) v = p.val_sorted[k];
+        const uint32_t range = (uint32_t)(v >> 32), gid = (uint32_t)v;
+        // 1. mark (leaf, k) in the bit matrix: order-free
+        for_each_leaf(p, T, s_leaf, range, gid, [&](int leaf, int owner, uint32_t) { atomicOr(mybits + leaf, 1u << owner); });
+        __syncthreads();
+        // 2. every instance finds its place: instances of the same leaf in earlier 32-entry groups of the chunk, then
+        //    the earlier lanes of its own group (bit order = depth order)
+        const uint32_t* row = p.matrix + (int64_t)c * nl;
+        for_each_leaf(p, T, s_leaf, range, gid, [&](int leaf, int owner, uint32_t og) {
+            uint32_t pos = __ldg(aux + leaf) + __ldg(row + leaf) + (uint32_t)__popc(mybits[leaf] & ((1u << owner) - 1u));
+            for (int w2 = 0; w2 < w; ++w2) pos += (uint32_t)__popc(s_bits[w2 * nl + leaf]);
+            p.inst_gid[pos] = og;
+        });
+        __syncthreads();
+        // 3. clear exactly the words that were touched (plain stores of 0: racing writers agree)
+        for_each_leaf(p, T, s_leaf, range, gid, [&](int leaf, int, uint32_t) { mybits[leaf] = 0u; });
+        __syncthreads();
     }
 }
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+int ms_grid(int32_t chunks, int32_t& per_cta) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int want = sms * 4;
+    per_cta = (chunks + want - 1) / want;
+    if (per_cta < 1) per_cta = 1;
+    return (chunks + per_cta - 1) / per_cta;
+}
+
 template <int C>
 int launch_multisplit(const MsParams& p, int32_t chunks, cudaStream_t st) {
-    const size_t common = ((size_t)6 * p.n1 + ((size_t)1 << (2 * p.base_level))) * sizeof(int32_t);
-    const size_t smem_count = common + (size_t)p.leaf_cap * sizeof(uint32_t);
-    const size_t smem_scatter = common + ((size_t)C + (size_t)(C / 32) * p.leaf_cap) * sizeof(uint32_t);
-    if (smem_scatter > 200 * 1024) { g2pc_set_error("g2pc_multisplit: shared memory budget exceeded"); return G2PC_ERR_INVALID; }
+    const size_t common = p.grid_w > 0 ? 0 : ((size_t)6 * p.n1 + ((size_t)1 << (2 * p.base_level))) * sizeof(int32_t);
+    const size_t smem_count = common + (size_t)2 * p.leaf_cap * sizeof(uint32_t);
+    const size_t smem_scatter = common + (size_t)(C / 32) * p.leaf_cap * sizeof(uint32_t);
+    if (smem_scatter > 200 * 1024 || smem_count > 200 * 1024) {
+        g2pc_set_error("g2pc_multisplit: shared memory budget exceeded");
+        return G2PC_ERR_INVALID;
+    }
     if (smem_count > 48 * 1024)
         G2PC_CUDA(cudaFuncSetAttribute(ms_count_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
     if (smem_scatter > 48 * 1024)
         G2PC_CUDA(cudaFuncSetAttribute(ms_scatter_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
-    ms_count_kernel<C><<<(unsigned)chunks, C, smem_count, st>>>(p);
+    int32_t per_cta = 1;
+    const int grid = ms_grid(chunks, per_cta);
+    ms_count_kernel<C><<<(unsigned)grid, C, smem_count, st>>>(p, chunks, per_cta);
     G2PC_CHECK_LAUNCH();
     const int scan_grid = (p.leaf_cap + 31) / 32;
-    ms_scan_kernel<<<(unsigned)(scan_grid < 1 ? 1 : scan_grid), 1024, 0, st>>>(p, chunks);
+    ms_scan_kernel<<<(unsigned)(scan_grid < 1 ? 1 : scan_grid), 1024, 0, st>>>(p, chunks, grid);
     G2PC_CHECK_LAUNCH();
-    ms_scatter_kernel<C><<<(unsigned)chunks, C, smem_scatter, st>>>(p);
+    ms_scatter_kernel<C><<<(unsigned)grid, C, smem_scatter, st>>>(p, chunks, per_cta);
     G2PC_CHECK_LAUNCH();
     return G2PC_OK;
 }
@@ -489,6 +535,15 @@ extern "C" int32_t g2pc_multisplit_chunk(int32_t leaf_cap) {
     return 0;
 }
 
+extern "C" int32_t g2pc_multisplit_rows(int64_t n, int32_t leaf_cap) {
+    // matrix rows the multisplit needs for n entries: one per chunk + one per segment (persistent CTA)
+    const int C = g2pc_multisplit_chunk(leaf_cap);
+    if (C <= 0) return 0;
+    const int32_t chunks = (int32_t)((n + C - 1) / C);
+    int32_t per_cta = 1;
+    return chunks + ms_grid(chunks, per_cta);
+}
+
 extern "C" int g2pc_multisplit(const uint64_t* val_sorted, int64_t n, const void* proj, int32_t width, int32_t height,
                                const int32_t* tables, int32_t num_levels, uint32_t level_mask, const int32_t* node_leaf,
                                const g2pc_leaf_t* leaves, const int32_t* header, int32_t leaf_cap, uint32_t* matrix,
@@ -509,7 +564,34 @@ extern "C" int g2pc_multisplit(const uint64_t* val_sorted, int64_t n, const void
     p.level_mask = level_mask; p.base_level = __builtin_ctz(level_mask);
     G2PC_CHECK_ARG(p.base_level <= G2PC_RANGE_MAX_LEVEL, "first leaf-candidate level too deep");
     p.node_leaf = node_leaf; p.header = header; p.leaves = leaves; p.matrix = matrix; p.inst_gid = inst_gid;
-    p.leaf_cap = leaf_cap;
+    p.leaf_cap = leaf_cap; p.grid_w = 0;
+    const int32_t chunks = (int32_t)((n + C - 1) / C);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 256) return launch_multisplit<256>(p, chunks, st);
+    if (C == 128) return launch_multisplit<128>(p, chunks, st);
+    return launch_multisplit<64>(p, chunks, st);
+}
+
+/* The same multisplit over a flat grid of tiles (s7_tiles.cu): leaf = tile index, the packed range is the tile rect. */
+extern "C" int g2pc_multisplit_grid(const uint64_t* val_sorted, int64_t n, int32_t grid_w, int32_t grid_h,
+                                    const g2pc_leaf_t* leaves, const int32_t* header, int32_t leaf_cap, uint32_t* matrix,
+                                    uint32_t* inst_gid, void* stream) {
+    G2PC_CHECK_ARG(n >= 0, "n < 0");
+    if (n == 0) return G2PC_OK;
+    G2PC_CHECK_ARG(val_sorted && leaves && header && matrix && inst_gid, "null pointer");
+    G2PC_CHECK_ARG(grid_w >= 1 && grid_h >= 1 && grid_w <= 256 && grid_h <= 256 && leaf_cap >= grid_w * grid_h,
+                   "bad tile grid / leaf_cap");
+    const int C = g2pc_multisplit_chunk(leaf_cap);
+    G2PC_CHECK_ARG(C > 0, "too many tiles for the multisplit");
+    MsParams p;
+    p.val_sorted = (const unsigned long long*)val_sorted; p.n = n; p.proj = nullptr;
+    p.width = 0; p.height = 0;
+    p.meta.num_levels = 1; p.meta.max_gaussians_per_tile = 0; p.meta.width = 0; p.meta.height = 0;
+    p.n1 = 0;
+    p.tab.xs = p.tab.xe = p.tab.xf = p.tab.ys = p.tab.ye = p.tab.yf = nullptr;
+    p.level_mask = 1u; p.base_level = 0;
+    p.node_leaf = nullptr; p.header = header; p.leaves = leaves; p.matrix = matrix; p.inst_gid = inst_gid;
+    p.leaf_cap = leaf_cap; p.grid_w = grid_w;
     const int32_t chunks = (int32_t)((n + C - 1) / C);
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 256) return launch_multisplit<256>(p, chunks, st);

@@ -42,13 +42,32 @@ SIGNATURES = {
     "g2pc_build_tree": ([_c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i32, _i64, _i64,
                          _i64, _i32, _i32, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
     "g2pc_multisplit_chunk": ([_i32], ctypes.c_int32),
+    "g2pc_multisplit_rows": ([_i64, _i32], ctypes.c_int32),
     "g2pc_multisplit": ([_c_void_p, _i64, _c_void_p, _i32, _i32, _c_void_p, _i32, _u32, _c_void_p, _c_void_p, _c_void_p,
                          _i32, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
     "g2pc_blend": ([_c_void_p, _c_void_p, _c_void_p, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                     _c_void_p, _i32, _i32, _f32, _f32, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
     "g2pc_accumulate": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p, _i32, _c_void_p], ctypes.c_int),
+    "g2pc_tiles_preprocess": ([_c_void_p, _c_void_p, _c_void_p, _i32, _i32, _i32, _i64, _c_void_p, _c_void_p, _c_void_p,
+                               _c_void_p, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_tiles_build": ([_c_void_p, _i32, _i32, _c_void_p, _c_void_p, _i32, _i64, _i64, _i32, _i32, _c_void_p,
+                          _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_multisplit_grid": ([_c_void_p, _i64, _i32, _i32, _c_void_p, _c_void_p, _i32, _c_void_p, _c_void_p, _c_void_p],
+                             ctypes.c_int),
+    "g2pc_tiles_blend": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                          _c_void_p, _c_void_p, _c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
+                         ctypes.c_int),
+    "g2pc_tiles_accumulate": ([_c_void_p, _c_void_p, _c_void_p, _i32, _i32, _i64, _c_void_p, _c_void_p, _c_void_p,
+                               _c_void_p, _c_void_p, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_fill_u32": ([_c_void_p, _u32, _i64, _c_void_p], ctypes.c_int),
     "g2pc_compose_image": ([_c_void_p, _c_void_p, _i32, _i32, _f32, _c_void_p, _c_void_p], ctypes.c_int),
 }
+
+
+class Raster(ctypes.Structure):
+    """g2pc_raster_t"""
+    _fields_ = [("viewmatrix", _f32 * 16), ("projmatrix", _f32 * 16), ("campos", _f32 * 3), ("tan_fovx", _f32),
+                ("tan_fovy", _f32), ("width", _i32), ("height", _i32)]
 
 
 class Camera(ctypes.Structure):
@@ -95,8 +114,9 @@ LAUNCHES = 0      # number of hand-written g2pc kernels launched since the last 
 TIMING = None     # None, or a dict filled as {entry point name: [(start_event, end_event), ...]}: every launch is
                   # bracketed with CUDA events on the current stream (bench.py)
 # hand-written kernels launched per entry point (default 1); the radix sort inside g2pc_depth_sort is cub's (library)
-_OWN_KERNELS = {"g2pc_multisplit": 3, "g2pc_depth_sort": 0}
-_NOT_KERNELS = {"g2pc_version", "g2pc_last_error", "g2pc_sample_emit_chunk_points", "g2pc_multisplit_chunk"}
+_OWN_KERNELS = {"g2pc_multisplit": 3, "g2pc_multisplit_grid": 3, "g2pc_depth_sort": 0}
+_NOT_KERNELS = {"g2pc_version", "g2pc_last_error", "g2pc_sample_emit_chunk_points", "g2pc_multisplit_chunk",
+                "g2pc_multisplit_rows"}
 
 
 def call(name, *args):

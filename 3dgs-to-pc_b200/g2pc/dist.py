@@ -138,10 +138,9 @@ def convert_gaussians_to_pc_sharded(scene, transforms, intrinsics, settings, ren
 
     rank, W = world()
     s = settings
-    if s.bounding_box_min is not None or s.bounding_box_max is not None or s.cull_large_percentage > 0.0 or \
-            s.surface_distance_std is not None or s.generate_mesh:
-        raise NotImplementedError("the sharded pipeline covers the visibility / opacity culls only; bounding boxes, "
-                                  "size culls, surface distances and meshing run through convert_gaussians_to_pc")
+    if s.cull_large_percentage > 0.0 or s.generate_mesh:
+        raise NotImplementedError("the sharded pipeline covers the visibility / opacity / bounding-box / surface-distance "
+                                  "culls; size-percentile culls and meshing run through convert_gaussians_to_pc")
     n_all = scene["xyz"].shape[0]
     gaussians = Gaussians(scene["xyz"], scene["scales"], scene["rots"], scene["colours"], scene["opacities"],
                           shs=scene.get("shs"))
@@ -153,7 +152,9 @@ def convert_gaussians_to_pc_sharded(scene, transforms, intrinsics, settings, ren
     if s.render_colours:
         renderer = get_renderer(s.renderer_type, gaussians.xyz, torch.unsqueeze(torch.clone(gaussians.opacities), 1),
                                 gaussians.colours, gaussians.covariances, shs=gaussians.shs if render_shs else None,
-                                visible_gaussian_threshold=s.visibility_threshold)
+                                visible_gaussian_threshold=s.visibility_threshold,
+                                surface_distance_std=s.surface_distance_std,
+                                calculate_surface_distance=s.surface_distance_std is not None)
         names = list(transforms.keys())
         # the accumulate kernel records the index of the camera that raised each maximum (needed by the merge)
         first_cam = torch.full((n_all,), torch.iinfo(torch.int32).max, dtype=torch.int32, device=keep.device)
@@ -168,11 +169,23 @@ def convert_gaussians_to_pc_sharded(scene, transforms, intrinsics, settings, ren
             renderer(cam, camera_index=ci)
         renderer.flush()
         merge_colour_accumulators(renderer.gaussian_max_contribution, renderer.gaussian_colours, first_cam)
+        if s.renderer_type == "cuda" and W > 1:
+            # CUDA back-end extras (gaussian_pointcloud_rasterization/__init__.py:152-158): the total contribution is a
+            # SUM over cameras (float addition is re-associated across ranks: last-bit differences vs one process), the
+            # surface distance a MIN
+            dist.all_reduce(renderer.gaussian_total_contribution, op=dist.ReduceOp.SUM)
+            if s.surface_distance_std is not None:
+                dist.all_reduce(renderer.gaussian_min_surface_distance, op=dist.ReduceOp.MIN)
         gaussians.colours = renderer.get_gaussian_colours()
+        if s.surface_distance_std is not None:
+            keep &= renderer.get_gaussians_with_low_surface_distance()
         if s.remove_unrendered_gaussians:
             keep &= renderer.get_visible_gaussians()
         if s.min_opacity > 0.0:
             keep &= gaussians.opacities > s.min_opacity
+        for bound, cmp in ((s.bounding_box_min, torch.gt), (s.bounding_box_max, torch.lt)):
+            if bound is not None:
+                keep &= cmp(gaussians.xyz, torch.as_tensor(bound, dtype=gaussians.xyz.dtype, device=keep.device)).all(dim=1)
         if s.prioritise_visible_gaussians:
             contributions = renderer.get_total_gaussian_contributions()
         g2p.LAST_RENDER_STATS = {"stats": renderer._stats, "replays": renderer.replays}

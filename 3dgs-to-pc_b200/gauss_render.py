@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from g2pc import capi, config, quadtree
+from g2pc.frames import FrameQueue
 
 # SH constants kept for API parity with the reference module (gauss_render.py:9-38)
 C0 = 0.28209479177387814
@@ -34,7 +35,7 @@ def strip_symmetric(sym):
     return strip_lowerdiag(sym)
 
 
-class GaussPythonRenderer():
+class GaussPythonRenderer(FrameQueue):
     """B200 implementation of the reference's pure-torch tile renderer (same constructor arguments, attributes and
     getters as gauss_render.py:210-264).
 
@@ -103,10 +104,7 @@ class GaussPythonRenderer():
         self._leaf_colour = None
         self._matrix = None
         self._inst_cap = max(8 * n, 1 << 16)
-        self._frame = 0
-        self._pending = []   # frames enqueued but not yet confirmed: (frame, camera, camera_index, pinned header, event)
-        self._hdr_pool = []
-        self.replays = 0
+        self._init_frames()
         self.last_stats = {}
 
     # ---- getters (gauss_render.py:237-264) -----------------------------------------------------------------
@@ -166,7 +164,7 @@ class GaussPythonRenderer():
         if chunk <= 0:
             raise capi.G2pcError(f"the quadtree has more than {cap} leaves: too many for the multisplit tables")
         t["leaf_cap"], t["chunk"] = cap, chunk
-        t["chunks"] = (self._n + chunk - 1) // chunk
+        t["chunks"] = int(self.lib.g2pc_multisplit_rows(self._n, cap))  # matrix rows: chunks + persistent CTAs
         t["leaves"] = torch.zeros((cap, capi.LEAF_WORDS), dtype=torch.int32, device=self.device)
         t["leaf_order"] = torch.zeros((cap,), dtype=torch.int32, device=self.device)
 
@@ -246,19 +244,7 @@ class GaussPythonRenderer():
     def __call__(self, camera, camera_index=None, **kwargs):
         """Render one camera and update the per-Gaussian accumulators (gauss_render.py:404-465).
         Returns (image (H,W,3) f32 flipped left-right | None, None, None, None)."""
-        frame = self._frame
-        self._frame += 1
-        camera_index = frame if camera_index is None else camera_index
-        t = self._enqueue(camera, frame, camera_index)
-        hdr = self._hdr_pool.pop() if self._hdr_pool else torch.zeros((capi.HDR_WORDS,), dtype=torch.int32).pin_memory()
-        hdr.copy_(self._hdr, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.device))
-        self._pending.append((frame, camera, camera_index, hdr, ev))
-        if not self.async_mode:
-            self.flush()
-        else:
-            self._poll(block_if_more_than=8)
+        self._submit(camera, camera_index)
         if not self.compose_image:
             return None, None, None, None
         t = self._last_tables  # (a replay may have switched to a deeper table set)
@@ -266,40 +252,15 @@ class GaussPythonRenderer():
         # final once flush() has run and is overwritten by the next camera)
         return (t["image"] if self.async_mode else t["image"].clone()), None, None, None
 
-    # ---- confirmation / recovery ---------------------------------------------------------------------------------
-    def _poll(self, block_if_more_than=None):
-        while self._pending:
-            frame, camera, cidx, hdr, ev = self._pending[0]
-            if not ev.query():
-                if block_if_more_than is None or len(self._pending) <= block_if_more_than:
-                    return
-                ev.synchronize()
-            h = hdr.tolist()
-            if h[capi.HDR_POISON]:
-                self._recover(h)
-                continue
-            self._confirm(h)
-            self._hdr_pool.append(hdr)
-            self._pending.pop(0)
-
+    # ---- FrameQueue hooks ---------------------------------------------------------------------------------------------
     def _confirm(self, h):
         t = self._last_tables
         self.last_stats = dict(num_leaves=h[capi.HDR_NUM_LEAVES],
                                total_instances=h[capi.HDR_TOTAL_INST] + (h[capi.HDR_TOTAL_INST_HI] << 32),
                                total_leaf_pixels=h[capi.HDR_TOTAL_PIX], levels=t["qt"].num_levels, frame=h[capi.HDR_FRAME])
 
-    def flush(self):
-        """Wait for every enqueued frame and replay the ones a poisoned header skipped."""
-        while self._pending:
-            self._pending[-1][4].synchronize()
-            self._poll(block_if_more_than=0)
-
-    def _recover(self, h):
-        """A frame did not fit: everything from that frame on was skipped on the device.  Grow, clear, replay."""
-        torch.cuda.current_stream(self.device).synchronize()
-        failed = h[capi.HDR_POISON] - 1
-        todo = [p for p in self._pending if p[0] >= failed]
-        self._pending = [p for p in self._pending if p[0] < failed]
+    def _fix(self, h):
+        """A frame did not fit: grow what was too small (everything from that frame on was skipped on the device)."""
         t = self._last_tables
         W, H = t["qt"].width, t["qt"].height
         if h[capi.HDR_NEED_DEEPER]:
@@ -323,16 +284,8 @@ class GaussPythonRenderer():
             t["pix_cap"] = max(t["pix_cap"], int(1.25 * h[capi.HDR_TOTAL_PIX]) + 1024)
         else:
             raise capi.G2pcError("poisoned frame header without a cause")
-        self._hdr.zero_()
         for tt in self._tables.values():
             tt["node_cnt"].zero_()
-        self.replays += 1
-        for (frame, camera, cidx, hdr, ev) in todo:
-            self._enqueue(camera, frame, cidx)
-            hdr.copy_(self._hdr, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(self.device))
-            self._pending.append((frame, camera, cidx, hdr, ev))
 
     # ---- introspection for the parity tests ---------------------------------------------------------------------
     def debug_last_camera(self):
@@ -355,8 +308,15 @@ def get_renderer(renderer_type: str, xyz, opacities, colours, covariances, shs=N
         return GaussPythonRenderer(xyz, opacities.type(torch.float), colours if shs is None else None, covariances,
                                    visible_gaussian_threshold=visible_gaussian_threshold, shs=shs)
     if renderer_type == "cuda":
-        raise NotImplementedError(
-            "renderer_type='cuda' (16x16-tile semantics of the reference's CUDA extension, incl. surface distances) is "
-            "the next row of the scope table (SURVEY.md §8f N2) and is not built yet; use renderer_type='python', "
-            "which runs the python renderer's semantics as B200 kernels")
+        # the reference's CUDA back-end semantics (16x16 tiles, alpha / transmittance cut-offs, depth maps, surface
+        # distances) on the sm_100a kernels of csrc/s7_tiles.cu — gauss_render.py:469-488
+        from g2pc.rasterizer import GaussianRasterizer as GaussianPCRasterizer
+        means2D = None  # (the reference allocates a zero tensor nobody reads, :476)
+        common = dict(cov3D_precomp=covariances.to(torch.float), visible_gaussian_threshold=visible_gaussian_threshold,
+                      surface_distance_std=surface_distance_std, calculate_surface_distance=calculate_surface_distance)
+        if shs is None:
+            return GaussianPCRasterizer(xyz.to(torch.float), means2D, opacities.type(torch.float),
+                                        colors_precomp=colours.to(torch.float), **common)
+        return GaussianPCRasterizer(xyz.to(torch.float), means2D, opacities.type(torch.float), shs=shs.to(torch.float),
+                                    sh_layout=0, **common)
     raise Exception(f"Renderer of type {renderer_type} is not supported")

@@ -66,7 +66,11 @@ def run(scene, cams, intr, device="cuda:0", pinned_tiles=(60, 60000), **settings
     saved = (g2p.load_gaussians, g2p.load_transform_data)
     g2p.load_gaussians, g2p.load_transform_data = load_gaussians, load_transform_data
     st = settings(ref, device=dev, **settings_kw)
-    ctx = contextlib.nullcontext() if on_gpu else ref_shim.cpu_redirect(pinned_tiles)
+    ctx = contextlib.ExitStack()
+    if not on_gpu:
+        ctx.enter_context(ref_shim.cpu_redirect(pinned_tiles))
+    if st.renderer_type == "cuda":
+        ctx.enter_context(ref_shim.reference_extension())  # the reference's own package, not the product's namesake
     try:
         with ctx:
             if on_gpu:

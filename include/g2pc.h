@@ -208,9 +208,11 @@ int g2pc_build_tree(const int32_t* tables, int32_t num_levels, int32_t max_gauss
 
 /* S4c.  Stable multisplit of the depth-ordered stream into the leaves' lists: inst_gid[leaf.inst_begin ..
  * + leaf.inst_count) = Gaussian ids overlapping the leaf, nearest first.  Three kernels (count, scan, scatter) over
- * chunks of C = g2pc_multisplit_chunk(leaf_cap) sorted entries; matrix: ceil(n / C) x leaves uint32 scratch.
+ * chunks of C = g2pc_multisplit_chunk(leaf_cap) sorted entries; matrix: g2pc_multisplit_rows(n, leaf_cap) x leaves
+ * uint32 scratch (pass that row count as ms_chunks to g2pc_build_tree, which checks the capacity).
  * leaf_cap = max_leaves given to g2pc_build_tree. */
 int32_t g2pc_multisplit_chunk(int32_t leaf_cap);
+int32_t g2pc_multisplit_rows(int64_t n, int32_t leaf_cap); /* rows of `matrix` needed (chunks + one per persistent CTA) */
 int g2pc_multisplit(const uint64_t* val_sorted, int64_t n, const void* proj, int32_t width, int32_t height,
                     const int32_t* tables, int32_t num_levels, uint32_t level_mask, const int32_t* node_leaf,
                     const g2pc_leaf_t* leaves, const int32_t* header, int32_t leaf_cap, uint32_t* matrix,
@@ -243,6 +245,62 @@ int g2pc_accumulate(uint64_t* cam_best, const float* leaf_colour, int64_t n, flo
 /* Rendered image (H,W,3) f32, flipped left-right like the reference (gauss_render.py:402); clears `owner`. */
 int g2pc_compose_image(uint32_t* owner, const float* leaf_colour, int32_t width, int32_t height, float background,
                        float* image, void* stream);
+
+/* ---- colour stage, renderer_type=cuda semantics: the reference's CUDA rasterizer restated (16x16 tiles) ---------- */
+/* Replaces _C.rasterize_gaussians (gaussian-pointcloud-rasterization/ext.cpp:15-17, rasterize_points.cu:36-145 ->
+ * CudaRasterizer::Rasterizer::forward, rasterizer_impl.cu:197-352: preprocessCUDA forward.cu:153-271, duplicateWithKeys /
+ * radix sort / identifyTileRanges rasterizer_impl.cu:69-137,285-326, renderCUDA forward.cu:303-497) and the accumulator
+ * updates of GaussianRasterizer.forward (gaussian_pointcloud_rasterization/__init__.py:126-158).
+ * One camera = tiles_preprocess -> depth_sort -> tiles_build -> multisplit_grid -> tiles_blend -> tiles_accumulate. */
+typedef struct {
+    float viewmatrix[16];  /* world->view, row-vector convention, z forward (camera_handler.py:75,91), row-major */
+    float projmatrix[16];  /* viewmatrix @ projection (camera_handler.py:100), row-major */
+    float campos[3];
+    float tan_fovx, tan_fovy;
+    int32_t width, height;
+} g2pc_raster_t;
+
+/* preprocessCUDA: near cull z_view <= 0.2, EWA covariance + 0.3, conic, radius = ceil(3 sqrt(lambda_max)), tile rect
+ * (16x16 tiles), colour given or SH deg <= 3 (sh_layout 0: (n,3,stride) channel-major as the loader yields it,
+ * gauss_dataloader.py:42-44; 1: (n,stride,3) coefficient-major as forward.cu:31 reads it).  Outputs as g2pc_preprocess
+ * (proj records, depth_key = bits(z_view), val = packed tile rect << 32 | index, node_cnt = Gaussians per tile);
+ * radii (n) int32 or NULL. */
+int g2pc_tiles_preprocess(const void* geom, const float* colours, const float* shs, int32_t sh_stride,
+                          int32_t sh_degree, int32_t sh_layout, int64_t n, const g2pc_raster_t* rs_host, void* proj,
+                          uint32_t* node_cnt, uint32_t* depth_key, uint64_t* val, int32_t* radii, void* stream);
+
+/* Tile table: every tile of the ceil(W/16) x ceil(H/16) grid is a leaf (leaf index = tile index, row-major); list
+ * offsets, launch order, frame header / poison as g2pc_build_tree; clears node_cnt and work_counters. */
+int g2pc_tiles_build(uint32_t* node_cnt, int32_t width, int32_t height, g2pc_leaf_t* leaves, int32_t* leaf_order,
+                     int32_t max_leaves, int64_t inst_capacity, int64_t matrix_capacity, int32_t ms_rows, int32_t frame,
+                     int32_t* header, int32_t* work_counters, void* stream);
+
+/* g2pc_multisplit over the tile grid (the packed range is the tile rect). */
+int g2pc_multisplit_grid(const uint64_t* val_sorted, int64_t n, int32_t grid_w, int32_t grid_h,
+                         const g2pc_leaf_t* leaves, const int32_t* header, int32_t leaf_cap, uint32_t* matrix,
+                         uint32_t* inst_gid, void* stream);
+
+/* renderCUDA: per pixel front-to-back blend (power > 0 and alpha < 1/255 skipped, the pixel stops before T < 1e-4),
+ * out_color (3,H,W) = C + T*bg, out_depth / out_invdepth (H,W) = sum depth*alpha*T / sum alpha*T/depth, written for
+ * pixels inside the image whose mask (H*W int32 or NULL) is non-zero; cam_best[g] = max((bits(alpha*T) << 32) |
+ * ~pixel_id) (deterministic arg-max: lowest pixel id among equals); cam_dist (n uint32, pre-filled with the bits of
+ * FLT_MAX, or NULL): bits of the minimum surface distance (see s7_tiles.cu header). */
+int g2pc_tiles_blend(const g2pc_leaf_t* leaves, const int32_t* leaf_order, const int32_t* header,
+                     const uint32_t* inst_gid, const void* proj, uint64_t* cam_best, uint32_t* cam_dist,
+                     const int32_t* mask, float* out_color, float* out_depth, float* out_invdepth, int32_t width,
+                     int32_t height, const float* background3_host, int32_t* work_counters, uint64_t* stats,
+                     void* stream);
+
+/* Accumulator update of one camera (__init__.py:128-158): where the camera's contribution beats max_contrib (strict >)
+ * store it and the FINAL colour of its arg-max pixel; total_contrib += contribution; min_dist = min(min_dist, cam_dist).
+ * Clears cam_best / re-arms cam_dist.  Optional per-camera outputs of the op (n each): cam_contrib f32, cam_pixel i32,
+ * cam_surface f32. */
+int g2pc_tiles_accumulate(uint64_t* cam_best, uint32_t* cam_dist, const float* out_color, int32_t width, int32_t height,
+                          int64_t n, float* max_contrib, float* total_contrib, float* colours, float* min_dist,
+                          int32_t* first_frame, int32_t frame, float* cam_contrib, int32_t* cam_pixel,
+                          float* cam_surface, void* stream);
+
+int g2pc_fill_u32(uint32_t* v, uint32_t value, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -115,6 +115,57 @@ def _stub_modules():
             sys.modules[name] = m
 
 
+_ref_ext = None
+
+
+def _load_reference_extension():
+    """The reference's OWN package `gaussian_pointcloud_rasterization` (wrapper + _C built by baseline/build_ref.py),
+    imported from baseline/_ref under a private module object — the product ships a package of the same name."""
+    global _ref_ext
+    if _ref_ext is not None:
+        return _ref_ext
+    import importlib.util
+    pkg_dir = os.path.join(STAGED_EXT_ROOT, "gaussian_pointcloud_rasterization")
+    init = os.path.join(pkg_dir, "__init__.py")
+    if not os.path.isfile(init):
+        return None
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "gaussian_pointcloud_rasterization"
+             or k.startswith("gaussian_pointcloud_rasterization.")}
+    try:
+        spec = importlib.util.spec_from_file_location("gaussian_pointcloud_rasterization", init,
+                                                      submodule_search_locations=[pkg_dir])
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["gaussian_pointcloud_rasterization"] = mod
+        spec.loader.exec_module(mod)  # imports ._C from pkg_dir
+        _ref_ext = {k: v for k, v in sys.modules.items() if k == "gaussian_pointcloud_rasterization"
+                    or k.startswith("gaussian_pointcloud_rasterization.")}
+    finally:
+        for k in list(sys.modules):
+            if k == "gaussian_pointcloud_rasterization" or k.startswith("gaussian_pointcloud_rasterization."):
+                sys.modules.pop(k)
+        sys.modules.update(saved)
+    return _ref_ext
+
+
+@contextlib.contextmanager
+def reference_extension():
+    """Inside the context `import gaussian_pointcloud_rasterization` (the reference imports it lazily: gauss_render.py:470,
+    camera_handler.py:73) resolves to the REFERENCE's package, not the product's."""
+    ext = _load_reference_extension()
+    if ext is None:
+        raise RuntimeError("reference CUDA extension not staged (baseline/build_ref.py)")
+    names = [k for k in sys.modules if k == "gaussian_pointcloud_rasterization"
+             or k.startswith("gaussian_pointcloud_rasterization.")]
+    saved = {k: sys.modules.pop(k) for k in names}
+    sys.modules.update(ext)
+    try:
+        yield ext["gaussian_pointcloud_rasterization"]
+    finally:
+        for k in ext:
+            sys.modules.pop(k, None)
+        sys.modules.update(saved)
+
+
 _loaded = None
 
 
@@ -131,10 +182,6 @@ def load():
              "mask_dataloader", "gauss_to_pc"]
     saved_mods = {n: sys.modules.pop(n) for n in names if n in sys.modules}
     sys.path.insert(0, REF_ROOT)
-    # the reference's CUDA extension package (gauss_render.py:470 imports it lazily) — only present when built
-    ext_on_path = os.path.isdir(os.path.join(STAGED_EXT_ROOT, "gaussian_pointcloud_rasterization"))
-    if ext_on_path and STAGED_EXT_ROOT not in sys.path:
-        sys.path.append(STAGED_EXT_ROOT)
     try:
         mods = {n: importlib.import_module(n) for n in names}
     finally:
