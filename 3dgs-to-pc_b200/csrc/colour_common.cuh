@@ -21,6 +21,13 @@ __host__ __device__ __forceinline__ void g2pc_unpack_range(uint32_t r, int& xlo,
     xlo = (int)(r & 255u); xhi = (int)((r >> 8) & 255u); ylo = (int)((r >> 16) & 255u); yhi = (int)(r >> 24);
 }
 
+// Frame failure word shared by the frames in flight (uint32, 0xFFFFFFFF = none, else 1 + the LOWEST frame that did not fit):
+// every kernel of frame f does nothing iff f + 1 >= *fail.  Frames of two CUDA streams may be in flight at once, so a
+// later frame can fail before an earlier one has finished: the earlier one must still complete.
+__device__ __forceinline__ bool g2pc_frame_skipped(const uint32_t* fail, int frame) {
+    return (uint32_t)(frame + 1) >= *fail;
+}
+
 struct QtMeta {
     int32_t num_levels;  // tabulated levels 0..num_levels-1
     int32_t max_gaussians_per_tile;

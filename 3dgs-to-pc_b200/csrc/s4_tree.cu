@@ -19,10 +19,11 @@
 //   3. g2pc_multisplit      stable one-pass-per-chunk multisplit of the depth-ordered stream into the leaves' lists:
 //        count    CTA c takes 256 consecutive sorted entries and counts its instances per leaf (shared-memory histogram)
 //        scan     per leaf, exclusive prefix over the chunks (+ the leaf's list offset)          -> matrix[c][leaf]
-//        scatter  CTA c marks bit (leaf, k) for every instance in a shared-memory bit matrix (order-free atomicOr), then
-//                 one thread per leaf walks its 256 bits in order and appends the Gaussian ids at matrix[c][leaf]:
-//                 the lists come out depth-ordered without any sort of the ~7 N instances (the round-1 path emitted
-//                 (leaf, id) pairs and ran a 2-pass 20 M-pair radix sort per camera).
+//        scatter  CTA c marks bit (leaf, k) for every instance in a shared-memory bit matrix (order-free atomicOr); an
+//                 instance's place is matrix[c][leaf] + the set bits of its leaf before bit k (popc): the lists come out
+//                 depth-ordered without any sort of the ~7 N instances (the round-1 path emitted (leaf, id) pairs and
+//                 ran a 2-pass 20 M-pair radix sort per camera).  Splats that cover many tiles are walked by the whole
+//                 warp (colour_common.cuh warp_for_each_node).
 #include <cub/cub.cuh>
 #include "colour_common.cuh"
 
@@ -45,6 +46,7 @@ struct TreeParams {
     int32_t ms_chunks;
     int32_t frame;
     int32_t* header;         // G2PC_HDR_WORDS
+    uint32_t* fail;          // shared failure word (colour_common.cuh)
     int32_t* work_counters;  // G2PC_WORK_COUNTERS ints, cleared here for the blend of this frame
     int32_t nodes_2d;
 };
@@ -93,7 +95,10 @@ __global__ void __launch_bounds__(TB) tree_kernel(const TreeParams p) {
     __shared__ int s_warp[33];
     __shared__ int s_flags[2];
     __shared__ unsigned long long s_sort[SORT_CAP];
-    if (p.header[G2PC_HDR_POISON] != 0) return;  // an earlier frame failed: keep its header for the host
+    if (g2pc_frame_skipped(p.fail, p.frame)) {  // this or an earlier frame failed: report and do nothing
+        if (threadIdx.x == 0) { p.header[G2PC_HDR_POISON] = (int32_t)*p.fail; p.header[G2PC_HDR_FRAME] = p.frame; }
+        return;
+    }
     const int L = p.meta.num_levels;
     if (threadIdx.x == 0) { s_flags[0] = 0; s_flags[1] = 0; }
     __syncthreads();
@@ -230,7 +235,9 @@ __global__ void __launch_bounds__(TB) tree_kernel(const TreeParams p) {
         p.header[G2PC_HDR_LEAF_OVERFLOW] = s_flags[1];
         p.header[G2PC_HDR_CAP_OVERFLOW] = cap_over;
         p.header[G2PC_HDR_FRAME] = p.frame;
-        if (s_flags[0] | s_flags[1] | cap_over) p.header[G2PC_HDR_POISON] = p.frame + 1;
+        if (s_flags[0] | s_flags[1] | cap_over) atomicMin(p.fail, (uint32_t)(p.frame + 1));
+        const uint32_t f = *(volatile uint32_t*)p.fail;
+        p.header[G2PC_HDR_POISON] = f == 0xFFFFFFFFu ? 0 : (int32_t)f;
     }
 }
 
@@ -250,6 +257,8 @@ struct MsParams {
     int32_t base_level;
     const int32_t* node_leaf;
     const int32_t* header;
+    const uint32_t* fail;
+    int32_t frame;
     const g2pc_leaf_t* leaves;
     uint32_t* matrix;      // [chunk][num_leaves]: counts, then absolute list offsets (in place)
     uint32_t* inst_gid;
@@ -329,132 +338,147 @@ __device__ __forceinline__ int32_t* ms_load_common(const MsParams& p, int32_t* s
     return s_leaf;
 }
 
-// CTA b owns the contiguous chunks [b * per_cta, (b + 1) * per_cta) ("segment" b).
-// count:   matrix[c][leaf] = instances of `leaf` in the chunks of the segment BEFORE c (running total in shared memory),
-//          aux[b][leaf] = instances of the whole segment;  scan: aux -> absolute list offset of the segment's first
-//          instance;  scatter: position = aux[b][leaf] + matrix[c][leaf] + rank inside the chunk.
+// count:   matrix[c][leaf] = instances of `leaf` in chunk c (one CTA per chunk of C sorted entries)
+// scan:    per leaf, exclusive prefix over the chunks + the leaf's list offset (three small kernels, 32 x 32 tiles)
+// scatter: position = matrix[c][leaf] + rank inside the chunk (bit matrix)
 template <int C>
-__global__ void __launch_bounds__(C) ms_count_kernel(const MsParams p, int32_t chunks, int32_t per_cta) {
+__global__ void __launch_bounds__(C) ms_count_kernel(const MsParams p) {
     extern __shared__ int32_t smem_ms[];
-    if (p.header[G2PC_HDR_POISON] != 0) return;
+    if (g2pc_frame_skipped(p.fail, p.frame)) return;
     const int nl = p.header[G2PC_HDR_NUM_LEAVES];
     QtTables T;
     int32_t* s_leaf = ms_load_common(p, smem_ms, T);
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_leaf + (p.grid_w > 0 ? 0 : (1 << (2 * p.base_level))));  // this chunk
-    uint32_t* s_run = s_hist + p.leaf_cap;                                              // earlier chunks of the segment
-    for (int i = threadIdx.x; i < nl; i += C) { s_hist[i] = 0u; s_run[i] = 0u; }
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_leaf + (p.grid_w > 0 ? 0 : (1 << (2 * p.base_level))));
+    for (int i = threadIdx.x; i < nl; i += C) s_hist[i] = 0u;
     __syncthreads();
-    const int c0 = blockIdx.x * per_cta, c1 = min(chunks, c0 + per_cta);
-    for (int c = c0; c < c1; ++c) {
-        const int64_t k = (int64_t)c * C + threadIdx.x;
-        unsigned long long v = (unsigned long long)G2PC_RANGE_EMPTY << 32;
-        if (k < p.n) v = p.val_sorted[k];
-        for_each_leaf(p, T, s_leaf, (uint32_t)(v >> 32), (uint32_t)v,
-                      [&](int leaf, int, uint32_t) { atomicAdd(s_hist + leaf, 1u); });
-        __syncthreads();
-        uint32_t* row = p.matrix + (int64_t)c * nl;
-        for (int i = threadIdx.x; i < nl; i += C) {
-            const uint32_t h = s_hist[i], r = s_run[i];
-            row[i] = r;
-            s_run[i] = r + h;
-            s_hist[i] = 0u;
-        }
-        __syncthreads();
-    }
-    uint32_t* aux = p.matrix + (int64_t)chunks * nl + (int64_t)blockIdx.x * nl;
-    for (int i = threadIdx.x; i < nl; i += C) aux[i] = s_run[i];
+    const int64_t k = (int64_t)blockIdx.x * C + threadIdx.x;
+    unsigned long long v = (unsigned long long)G2PC_RANGE_EMPTY << 32;
+    if (k < p.n) v = p.val_sorted[k];
+    for_each_leaf(p, T, s_leaf, (uint32_t)(v >> 32), (uint32_t)v,
+                  [&](int leaf, int, uint32_t) { atomicAdd(s_hist + leaf, 1u); });
+    __syncthreads();
+    uint32_t* row = p.matrix + (int64_t)blockIdx.x * nl;
+    for (int i = threadIdx.x; i < nl; i += C) row[i] = s_hist[i];
 }
 
-// per leaf (column) of `m` (rows x num_leaves): totals -> absolute offsets (exclusive prefix over the rows + the leaf's
-// list offset).  CTA = 32 leaves x 32 row groups; the matrix is read twice (sum, then rewrite).
-__global__ void __launch_bounds__(1024) ms_scan_kernel(const MsParams p, int32_t chunks, int32_t rows) {
+// Column-wise exclusive scan of matrix (rows x num_leaves) in three steps over tiles of 1024 rows x 32 leaves:
+//   partial: tile sums -> tile_sum[tile_row][leaf];  blocks: per leaf, scan of the tile sums + the leaf's list offset;
+//   apply: every tile rewrites its rows as running offsets.
+constexpr int SCAN_ROWS = 1024;  // rows per tile (32 per thread)
+__global__ void __launch_bounds__(1024) ms_scan_partial_kernel(const MsParams p, int32_t rows) {
     __shared__ uint32_t s_sum[32][33];
-    if (p.header[G2PC_HDR_POISON] != 0) return;
+    if (g2pc_frame_skipped(p.fail, p.frame)) return;
     const int nl = p.header[G2PC_HDR_NUM_LEAVES];
-    uint32_t* __restrict__ m = p.matrix + (int64_t)chunks * nl;  // the segment totals written by the count kernel
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int seg = (rows + 31) / 32;
-    for (int leaf0 = blockIdx.x * 32; leaf0 < nl; leaf0 += gridDim.x * 32) {
-        const int leaf = leaf0 + tx;
-        const int r0 = min(rows, ty * seg), r1 = min(rows, r0 + seg);
-        uint32_t sum = 0;
-        if (leaf < nl)
-            for (int r = r0; r < r1; ++r) sum += m[(int64_t)r * nl + leaf];
-        s_sum[ty][tx] = sum;
-        __syncthreads();
-        if (ty == 0) {
-            uint32_t run = (leaf < nl) ? (uint32_t)p.leaves[leaf].inst_begin : 0u;
-            for (int s = 0; s < 32; ++s) { const uint32_t t = s_sum[s][tx]; s_sum[s][tx] = run; run += t; }
-        }
-        __syncthreads();
-        if (leaf < nl) {
-            uint32_t run = s_sum[ty][tx];
-            for (int r = r0; r < r1; ++r) {
-                uint32_t* c = m + (int64_t)r * nl + leaf;
-                const uint32_t t = *c;
-                *c = run;
-                run += t;
-            }
-        }
-        __syncthreads();
+    const int leaf = blockIdx.x * 32 + tx;
+    if (blockIdx.x * 32 >= nl) return;
+    const int r0 = blockIdx.y * SCAN_ROWS + ty * 32;
+    uint32_t sum = 0;
+    if (leaf < nl) {
+#pragma unroll 8
+        for (int r = r0; r < min(rows, r0 + 32); ++r) sum += p.matrix[(int64_t)r * nl + leaf];
+    }
+    s_sum[ty][tx] = sum;
+    __syncthreads();
+    if (ty == 0 && leaf < nl) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int s = 0; s < 32; ++s) t += s_sum[s][tx];
+        uint32_t* tile_sum = p.matrix + (int64_t)rows * nl;  // appended behind the rows
+        tile_sum[(int64_t)blockIdx.y * nl + leaf] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) ms_scan_blocks_kernel(const MsParams p, int32_t rows, int32_t tiles) {
+    if (g2pc_frame_skipped(p.fail, p.frame)) return;
+    const int nl = p.header[G2PC_HDR_NUM_LEAVES];
+    const int leaf = blockIdx.x * 256 + threadIdx.x;
+    if (leaf >= nl) return;
+    uint32_t* tile_sum = p.matrix + (int64_t)rows * nl;
+    uint32_t run = (uint32_t)p.leaves[leaf].inst_begin;
+    for (int t = 0; t < tiles; ++t) {
+        const uint32_t v = tile_sum[(int64_t)t * nl + leaf];
+        tile_sum[(int64_t)t * nl + leaf] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(1024) ms_scan_apply_kernel(const MsParams p, int32_t rows) {
+    __shared__ uint32_t s_sum[32][33];
+    if (g2pc_frame_skipped(p.fail, p.frame)) return;
+    const int nl = p.header[G2PC_HDR_NUM_LEAVES];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int leaf = blockIdx.x * 32 + tx;
+    if (blockIdx.x * 32 >= nl) return;
+    const int r0 = blockIdx.y * SCAN_ROWS + ty * 32, r1 = min(rows, r0 + 32);
+    uint32_t v[32];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+        v[q] = (leaf < nl && r0 + q < r1) ? p.matrix[(int64_t)(r0 + q) * nl + leaf] : 0u;
+        sum += v[q];
+    }
+    s_sum[ty][tx] = sum;
+    __syncthreads();
+    if (leaf >= nl) return;
+    const uint32_t* tile_sum = p.matrix + (int64_t)rows * nl;
+    uint32_t run = tile_sum[(int64_t)blockIdx.y * nl + leaf];
+    for (int s = 0; s < ty; ++s) run += s_sum[s][tx];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+        if (r0 + q < r1) p.matrix[(int64_t)(r0 + q) * nl + leaf] = run;
+        run += v[q];
     }
 }
 
 template <int C>
-__global__ void __launch_bounds__(C) ms_scatter_kernel(const MsParams p, int32_t chunks, int32_t per_cta) {
+__global__ void __launch_bounds__(C) ms_scatter_kernel(const MsParams p) {
     extern __shared__ int32_t smem_ms[];
-    if (p.header[G2PC_HDR_POISON] != 0) return;
+    if (g2pc_frame_skipped(p.fail, p.frame)) return;
     const int nl = p.header[G2PC_HDR_NUM_LEAVES];
     constexpr int WORDS = C / 32;
     QtTables T;
     int32_t* s_leaf = ms_load_common(p, smem_ms, T);
-    uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_leaf + (p.grid_w > 0 ? 0 : (1 << (2 * p.base_level))));  // [WORDS][nl], zero between chunks
-    for (int i = threadIdx.x; i < WORDS * nl; i += C) s_bits[i] = 0u;
+    uint32_t* s_row = reinterpret_cast<uint32_t*>(s_leaf + (p.grid_w > 0 ? 0 : (1 << (2 * p.base_level))));  // [nl]
+    uint32_t* s_bits = s_row + p.leaf_cap;                                                                   // [WORDS][nl]
+    {
+        // the chunk's list offsets (one coalesced row of the matrix) and a zeroed bit matrix; 16-byte stores where the
+        // carve-up allows (leaf_cap is a multiple of 4 and the dynamic smem base is 16-byte aligned)
+        const uint32_t* grow = p.matrix + (int64_t)blockIdx.x * nl;
+        for (int i = threadIdx.x; i < nl; i += C) s_row[i] = grow[i];
+        if (((reinterpret_cast<uintptr_t>(s_bits) & 15) == 0) && ((nl & 3) == 0)) {
+            uint4* b4 = reinterpret_cast<uint4*>(s_bits);
+            for (int i = threadIdx.x; i < WORDS * nl / 4; i += C) b4[i] = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+            for (int i = threadIdx.x; i < WORDS * nl; i += C) s_bits[i] = 0u;
+        }
+    }
     __syncthreads();
-    const uint32_t* aux = p.matrix + (int64_t)chunks * nl + (int64_t)blockIdx.x * nl;
     const int w = threadIdx.x >> 5;  // the warp = the 32-entry group of the chunk
     uint32_t* mybits = s_bits + w * nl;
-    const int c0 = blockIdx.x * per_cta, c1 = min(chunks, c0 + per_cta);
-    for (int c = c0; c < c1; ++c) {
-        const int64_t k = (int64_t)c * C + threadIdx.x;
-        unsigned long long v = (unsigned long long)G2PC_RANGE_EMPTY << 32;
-        if (k < p.n) v = p.val_sorted[k];
-        const uint32_t range = (uint32_t)(v >> 32), gid = (uint32_t)v;
-        // 1. mark (leaf, k) in the bit matrix: order-free
-        for_each_leaf(p, T, s_leaf, range, gid, [&](int leaf, int owner, uint32_t) { atomicOr(mybits + leaf, 1u << owner); });
-        __syncthreads();
-        // 2. every instance finds its place: instances of the same leaf in earlier 32-entry groups of the chunk, then
-        //    the earlier lanes of its own group (bit order = depth order)
-        const uint32_t* row = p.matrix + (int64_t)c * nl;
-        for_each_leaf(p, T, s_leaf, range, gid, [&](int leaf, int owner, uint32_t og) {
-            uint32_t pos = __ldg(aux + leaf) + __ldg(row + leaf) + (uint32_t)__popc(mybits[leaf] & ((1u << owner) - 1u));
-            for (int w2 = 0; w2 < w; ++w2) pos += (uint32_t)__popc(s_bits[w2 * nl + leaf]);
-            p.inst_gid[pos] = og;
-        });
-        __syncthreads();
-        // 3. clear exactly the words that were touched (plain stores of 0: racing writers agree)
-        for_each_leaf(p, T, s_leaf, range, gid, [&](int leaf, int, uint32_t) { mybits[leaf] = 0u; });
-        __syncthreads();
-    }
+    const int64_t k = (int64_t)blockIdx.x * C + threadIdx.x;
+    unsigned long long v = (unsigned long long)G2PC_RANGE_EMPTY << 32;
+    if (k < p.n) v = p.val_sorted[k];
+    const uint32_t range = (uint32_t)(v >> 32), gid = (uint32_t)v;
+    // 1. mark (leaf, k) in the bit matrix: order-free
+    for_each_leaf(p, T, s_leaf, range, gid, [&](int leaf, int owner, uint32_t) { atomicOr(mybits + leaf, 1u << owner); });
+    __syncthreads();
+    // 2. every instance finds its place: the chunk's offset for the leaf, the instances of the same leaf in earlier
+    //    32-entry groups of the chunk, then the earlier lanes of its own group (bit order = depth order)
+    for_each_leaf(p, T, s_leaf, range, gid, [&](int leaf, int owner, uint32_t og) {
+        uint32_t pos = s_row[leaf] + (uint32_t)__popc(mybits[leaf] & ((1u << owner) - 1u));
+        for (int w2 = 0; w2 < w; ++w2) pos += (uint32_t)__popc(s_bits[w2 * nl + leaf]);
+        p.inst_gid[pos] = og;
+    });
 }
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-int ms_grid(int32_t chunks, int32_t& per_cta) {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int want = sms * 4;
-    per_cta = (chunks + want - 1) / want;
-    if (per_cta < 1) per_cta = 1;
-    return (chunks + per_cta - 1) / per_cta;
-}
-
 template <int C>
 int launch_multisplit(const MsParams& p, int32_t chunks, cudaStream_t st) {
     const size_t common = p.grid_w > 0 ? 0 : ((size_t)6 * p.n1 + ((size_t)1 << (2 * p.base_level))) * sizeof(int32_t);
-    const size_t smem_count = common + (size_t)2 * p.leaf_cap * sizeof(uint32_t);
-    const size_t smem_scatter = common + (size_t)(C / 32) * p.leaf_cap * sizeof(uint32_t);
+    const size_t smem_count = common + (size_t)p.leaf_cap * sizeof(uint32_t);
+    const size_t smem_scatter = common + (size_t)(C / 32 + 1) * p.leaf_cap * sizeof(uint32_t);
     if (smem_scatter > 200 * 1024 || smem_count > 200 * 1024) {
         g2pc_set_error("g2pc_multisplit: shared memory budget exceeded");
         return G2PC_ERR_INVALID;
@@ -463,14 +487,17 @@ int launch_multisplit(const MsParams& p, int32_t chunks, cudaStream_t st) {
         G2PC_CUDA(cudaFuncSetAttribute(ms_count_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
     if (smem_scatter > 48 * 1024)
         G2PC_CUDA(cudaFuncSetAttribute(ms_scatter_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scatter));
-    int32_t per_cta = 1;
-    const int grid = ms_grid(chunks, per_cta);
-    ms_count_kernel<C><<<(unsigned)grid, C, smem_count, st>>>(p, chunks, per_cta);
+    ms_count_kernel<C><<<(unsigned)chunks, C, smem_count, st>>>(p);
     G2PC_CHECK_LAUNCH();
-    const int scan_grid = (p.leaf_cap + 31) / 32;
-    ms_scan_kernel<<<(unsigned)(scan_grid < 1 ? 1 : scan_grid), 1024, 0, st>>>(p, chunks, grid);
+    const int tiles = (chunks + SCAN_ROWS - 1) / SCAN_ROWS;
+    const dim3 sgrid((unsigned)((p.leaf_cap + 31) / 32), (unsigned)tiles);
+    ms_scan_partial_kernel<<<sgrid, 1024, 0, st>>>(p, chunks);
     G2PC_CHECK_LAUNCH();
-    ms_scatter_kernel<C><<<(unsigned)grid, C, smem_scatter, st>>>(p, chunks, per_cta);
+    ms_scan_blocks_kernel<<<(unsigned)((p.leaf_cap + 255) / 256), 256, 0, st>>>(p, chunks, tiles);
+    G2PC_CHECK_LAUNCH();
+    ms_scan_apply_kernel<<<sgrid, 1024, 0, st>>>(p, chunks);
+    G2PC_CHECK_LAUNCH();
+    ms_scatter_kernel<C><<<(unsigned)chunks, C, smem_scatter, st>>>(p);
     G2PC_CHECK_LAUNCH();
     return G2PC_OK;
 }
@@ -481,9 +508,9 @@ extern "C" int g2pc_build_tree(const int32_t* tables, int32_t num_levels, int32_
                                uint32_t* node_cnt, uint8_t* node_state, int32_t* node_leaf, g2pc_leaf_t* leaves,
                                int32_t* leaf_order, int32_t max_leaves, int64_t inst_capacity, int64_t pix_capacity,
                                int64_t matrix_capacity, int32_t ms_chunks, int32_t frame, int32_t* header,
-                               int32_t* work_counters, void* stream) {
-    G2PC_CHECK_ARG(tables && node_cnt && node_state && node_leaf && leaves && leaf_order && header && work_counters,
-                   "null pointer");
+                               uint32_t* fail, int32_t* work_counters, void* stream) {
+    G2PC_CHECK_ARG(tables && node_cnt && node_state && node_leaf && leaves && leaf_order && header && fail &&
+                       work_counters, "null pointer");
     G2PC_CHECK_ARG(num_levels >= 1 && num_levels <= G2PC_MAX_LEVELS && max_leaves >= 1, "bad sizes");
     G2PC_CHECK_ARG(frame >= 0 && ms_chunks >= 0, "bad frame / chunk count");
     TreeParams p;
@@ -495,7 +522,7 @@ extern "C" int g2pc_build_tree(const int32_t* tables, int32_t num_levels, int32_
     p.node_cnt = node_cnt; p.node_state = node_state; p.node_leaf = node_leaf; p.leaves = leaves;
     p.leaf_order = leaf_order; p.max_leaves = max_leaves;
     p.inst_capacity = inst_capacity; p.pix_capacity = pix_capacity; p.matrix_capacity = matrix_capacity;
-    p.ms_chunks = ms_chunks; p.frame = frame; p.header = header; p.work_counters = work_counters;
+    p.ms_chunks = ms_chunks; p.frame = frame; p.header = header; p.fail = fail; p.work_counters = work_counters;
     p.nodes_2d = ((1 << (2 * num_levels)) - 1) / 3;
     tree_kernel<<<1, TB, 0, (cudaStream_t)stream>>>(p);
     G2PC_CHECK_LAUNCH();
@@ -529,28 +556,28 @@ extern "C" int g2pc_depth_sort(const uint32_t* depth_key, const uint64_t* val, i
 
 extern "C" int32_t g2pc_multisplit_chunk(int32_t leaf_cap) {
     // entries per chunk: the scatter kernel keeps leaf_cap x chunk bits in shared memory
-    if ((int64_t)leaf_cap * 32 <= 160 * 1024) return 256;
-    if ((int64_t)leaf_cap * 16 <= 160 * 1024) return 128;
-    if ((int64_t)leaf_cap * 8 <= 160 * 1024) return 64;
+    if ((int64_t)leaf_cap * 36 <= 160 * 1024) return 256;
+    if ((int64_t)leaf_cap * 20 <= 160 * 1024) return 128;
+    if ((int64_t)leaf_cap * 12 <= 160 * 1024) return 64;
     return 0;
 }
 
 extern "C" int32_t g2pc_multisplit_rows(int64_t n, int32_t leaf_cap) {
-    // matrix rows the multisplit needs for n entries: one per chunk + one per segment (persistent CTA)
+    // matrix rows the multisplit needs for n entries: one per chunk + one per scan tile of 1024 chunks
     const int C = g2pc_multisplit_chunk(leaf_cap);
     if (C <= 0) return 0;
     const int32_t chunks = (int32_t)((n + C - 1) / C);
-    int32_t per_cta = 1;
-    return chunks + ms_grid(chunks, per_cta);
+    return chunks + (chunks + SCAN_ROWS - 1) / SCAN_ROWS;
 }
 
 extern "C" int g2pc_multisplit(const uint64_t* val_sorted, int64_t n, const void* proj, int32_t width, int32_t height,
                                const int32_t* tables, int32_t num_levels, uint32_t level_mask, const int32_t* node_leaf,
-                               const g2pc_leaf_t* leaves, const int32_t* header, int32_t leaf_cap, uint32_t* matrix,
-                               uint32_t* inst_gid, void* stream) {
+                               const g2pc_leaf_t* leaves, const int32_t* header, const uint32_t* fail, int32_t frame,
+                               int32_t leaf_cap, uint32_t* matrix, uint32_t* inst_gid, void* stream) {
     G2PC_CHECK_ARG(n >= 0, "n < 0");
     if (n == 0) return G2PC_OK;
-    G2PC_CHECK_ARG(val_sorted && proj && tables && node_leaf && leaves && header && matrix && inst_gid, "null pointer");
+    G2PC_CHECK_ARG(val_sorted && proj && tables && node_leaf && leaves && header && fail && matrix && inst_gid,
+                   "null pointer");
     G2PC_CHECK_ARG(num_levels >= 1 && num_levels <= G2PC_MAX_LEVELS && level_mask != 0u, "bad levels");
     const int C = g2pc_multisplit_chunk(leaf_cap);
     G2PC_CHECK_ARG(C > 0, "too many leaves for the multisplit");
@@ -563,7 +590,8 @@ extern "C" int g2pc_multisplit(const uint64_t* val_sorted, int64_t n, const void
     p.tab.ys = tables + 3 * p.n1; p.tab.ye = tables + 4 * p.n1; p.tab.yf = tables + 5 * p.n1;
     p.level_mask = level_mask; p.base_level = __builtin_ctz(level_mask);
     G2PC_CHECK_ARG(p.base_level <= G2PC_RANGE_MAX_LEVEL, "first leaf-candidate level too deep");
-    p.node_leaf = node_leaf; p.header = header; p.leaves = leaves; p.matrix = matrix; p.inst_gid = inst_gid;
+    p.node_leaf = node_leaf; p.header = header; p.fail = fail; p.frame = frame; p.leaves = leaves; p.matrix = matrix;
+    p.inst_gid = inst_gid;
     p.leaf_cap = leaf_cap; p.grid_w = 0;
     const int32_t chunks = (int32_t)((n + C - 1) / C);
     cudaStream_t st = (cudaStream_t)stream;
@@ -574,11 +602,11 @@ extern "C" int g2pc_multisplit(const uint64_t* val_sorted, int64_t n, const void
 
 /* The same multisplit over a flat grid of tiles (s7_tiles.cu): leaf = tile index, the packed range is the tile rect. */
 extern "C" int g2pc_multisplit_grid(const uint64_t* val_sorted, int64_t n, int32_t grid_w, int32_t grid_h,
-                                    const g2pc_leaf_t* leaves, const int32_t* header, int32_t leaf_cap, uint32_t* matrix,
-                                    uint32_t* inst_gid, void* stream) {
+                                    const g2pc_leaf_t* leaves, const int32_t* header, const uint32_t* fail,
+                                    int32_t frame, int32_t leaf_cap, uint32_t* matrix, uint32_t* inst_gid, void* stream) {
     G2PC_CHECK_ARG(n >= 0, "n < 0");
     if (n == 0) return G2PC_OK;
-    G2PC_CHECK_ARG(val_sorted && leaves && header && matrix && inst_gid, "null pointer");
+    G2PC_CHECK_ARG(val_sorted && leaves && header && fail && matrix && inst_gid, "null pointer");
     G2PC_CHECK_ARG(grid_w >= 1 && grid_h >= 1 && grid_w <= 256 && grid_h <= 256 && leaf_cap >= grid_w * grid_h,
                    "bad tile grid / leaf_cap");
     const int C = g2pc_multisplit_chunk(leaf_cap);
@@ -590,7 +618,8 @@ extern "C" int g2pc_multisplit_grid(const uint64_t* val_sorted, int64_t n, int32
     p.n1 = 0;
     p.tab.xs = p.tab.xe = p.tab.xf = p.tab.ys = p.tab.ye = p.tab.yf = nullptr;
     p.level_mask = 1u; p.base_level = 0;
-    p.node_leaf = nullptr; p.header = header; p.leaves = leaves; p.matrix = matrix; p.inst_gid = inst_gid;
+    p.node_leaf = nullptr; p.header = header; p.fail = fail; p.frame = frame; p.leaves = leaves; p.matrix = matrix;
+    p.inst_gid = inst_gid;
     p.leaf_cap = leaf_cap; p.grid_w = grid_w;
     const int32_t chunks = (int32_t)((n + C - 1) / C);
     cudaStream_t st = (cudaStream_t)stream;

@@ -41,6 +41,8 @@ struct BlendParams {
     const g2pc_leaf_t* leaves;
     const int32_t* leaf_order;
     const int32_t* header;
+    const uint32_t* fail;
+    int32_t frame;
     const uint32_t* inst_gid;
     const float4* proj;
     unsigned long long* cam_best;
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(BT, 8) blend_kernel(const BlendParams p) {
     __shared__ __align__(8) unsigned long long s_bar[3];
     __shared__ int s_item;
 
-    if (p.header[G2PC_HDR_POISON] != 0) return;
+    if (g2pc_frame_skipped(p.fail, p.frame)) return;
     const int num_items = p.header[G2PC_HDR_NUM_LEAVES] * p.slabs;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -330,17 +332,19 @@ __global__ void __launch_bounds__(256) compose_kernel(uint32_t* __restrict__ own
 }  // namespace
 
 extern "C" int g2pc_blend(const g2pc_leaf_t* leaves, const int32_t* leaf_order, const int32_t* header,
-                          int32_t max_leaf_pixels_quads, const uint32_t* inst_gid, const void* proj,
+                          const uint32_t* fail, int32_t frame, int32_t max_leaf_pixels_quads, const uint32_t* inst_gid,
+                          const void* proj,
                           uint64_t* cam_best, const float* max_contrib, float* leaf_colour, uint32_t* owner,
                           int32_t width, int32_t height, float background, float t_stop, int32_t* work_counters,
                           uint64_t* stats, void* stream) {
-    G2PC_CHECK_ARG(leaves && leaf_order && header && inst_gid && proj && cam_best && max_contrib && leaf_colour &&
+    G2PC_CHECK_ARG(leaves && leaf_order && header && fail && inst_gid && proj && cam_best && max_contrib && leaf_colour &&
                        owner && work_counters, "null pointer");
     G2PC_CHECK_ARG(max_leaf_pixels_quads >= 1, "max_leaf_pixels_quads < 1");
     G2PC_CHECK_ARG(t_stop >= 0.0f && t_stop < 1.0f, "t_stop must be in [0, 1)");
     G2PC_CHECK_ARG(((uintptr_t)inst_gid & 15) == 0, "inst_gid must be 16-byte aligned (TMA bulk copies)");
     BlendParams p;
-    p.leaves = leaves; p.leaf_order = leaf_order; p.header = header; p.inst_gid = inst_gid;
+    p.leaves = leaves; p.leaf_order = leaf_order; p.header = header; p.fail = fail; p.frame = frame;
+    p.inst_gid = inst_gid;
     p.proj = (const float4*)proj;
     p.cam_best = (unsigned long long*)cam_best; p.max_contrib = max_contrib; p.leaf_colour = leaf_colour;
     p.owner = owner;

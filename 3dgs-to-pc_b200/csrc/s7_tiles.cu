@@ -227,13 +227,17 @@ struct TileTreeParams {
     int64_t inst_capacity, matrix_capacity;
     int32_t ms_rows, frame;
     int32_t* header;
+    uint32_t* fail;
     int32_t* work_counters;
 };
 
 __global__ void __launch_bounds__(TB) tile_tree_kernel(const TileTreeParams p) {
     __shared__ int s_warp[33];
     __shared__ uint32_t s_sort[SORT_CAP];  // (2^19 - 1 - min(count, 2^19 - 1)) << 13 | tile
-    if (p.header[G2PC_HDR_POISON] != 0) return;
+    if (g2pc_frame_skipped(p.fail, p.frame)) {
+        if (threadIdx.x == 0) { p.header[G2PC_HDR_POISON] = (int32_t)*p.fail; p.header[G2PC_HDR_FRAME] = p.frame; }
+        return;
+    }
     const int nt = p.gx * p.gy;
     const int nl = nt < p.max_leaves ? nt : p.max_leaves;
     long long inst_total = 0;
@@ -298,7 +302,9 @@ __global__ void __launch_bounds__(TB) tile_tree_kernel(const TileTreeParams p) {
         p.header[G2PC_HDR_LEAF_OVERFLOW] = leaf_over;
         p.header[G2PC_HDR_CAP_OVERFLOW] = cap_over;
         p.header[G2PC_HDR_FRAME] = p.frame;
-        if (leaf_over | cap_over) p.header[G2PC_HDR_POISON] = p.frame + 1;
+        if (leaf_over | cap_over) atomicMin(p.fail, (uint32_t)(p.frame + 1));
+        const uint32_t f = *(volatile uint32_t*)p.fail;
+        p.header[G2PC_HDR_POISON] = f == 0xFFFFFFFFu ? 0 : (int32_t)f;
     }
 }
 
@@ -312,6 +318,8 @@ struct TileBlendParams {
     const g2pc_leaf_t* leaves;
     const int32_t* leaf_order;
     const int32_t* header;
+    const uint32_t* fail;
+    int32_t frame;
     const uint32_t* inst_gid;
     const float4* proj;
     unsigned long long* cam_best;
@@ -372,7 +380,7 @@ __global__ void __launch_bounds__(TBT, 12) blend_tiles_kernel(const TileBlendPar
     __shared__ float s_rdepth[SURF ? 256 : 1];    // depths / ids of the current round's entries
     __shared__ uint32_t s_rgid[SURF ? 256 : 1];
 
-    if (p.header[G2PC_HDR_POISON] != 0) return;
+    if (g2pc_frame_skipped(p.fail, p.frame)) return;
     const int num_items = p.header[G2PC_HDR_NUM_LEAVES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -651,29 +659,31 @@ extern "C" int g2pc_tiles_preprocess(const void* geom, const float* colours, con
 
 extern "C" int g2pc_tiles_build(uint32_t* node_cnt, int32_t width, int32_t height, g2pc_leaf_t* leaves,
                                 int32_t* leaf_order, int32_t max_leaves, int64_t inst_capacity, int64_t matrix_capacity,
-                                int32_t ms_rows, int32_t frame, int32_t* header, int32_t* work_counters, void* stream) {
-    G2PC_CHECK_ARG(node_cnt && leaves && leaf_order && header && work_counters, "null pointer");
+                                int32_t ms_rows, int32_t frame, int32_t* header, uint32_t* fail, int32_t* work_counters,
+                                void* stream) {
+    G2PC_CHECK_ARG(node_cnt && leaves && leaf_order && header && fail && work_counters, "null pointer");
     G2PC_CHECK_ARG(width > 0 && height > 0 && max_leaves >= 1 && frame >= 0, "bad sizes");
     TileTreeParams p;
     p.node_cnt = node_cnt; p.leaves = leaves; p.leaf_order = leaf_order;
     p.W = width; p.H = height; p.gx = (width + TILE - 1) / TILE; p.gy = (height + TILE - 1) / TILE;
     p.max_leaves = max_leaves; p.inst_capacity = inst_capacity; p.matrix_capacity = matrix_capacity;
-    p.ms_rows = ms_rows; p.frame = frame; p.header = header; p.work_counters = work_counters;
+    p.ms_rows = ms_rows; p.frame = frame; p.header = header; p.fail = fail; p.work_counters = work_counters;
     tile_tree_kernel<<<1, TB, 0, (cudaStream_t)stream>>>(p);
     G2PC_CHECK_LAUNCH();
     return G2PC_OK;
 }
 
 extern "C" int g2pc_tiles_blend(const g2pc_leaf_t* leaves, const int32_t* leaf_order, const int32_t* header,
-                                const uint32_t* inst_gid, const void* proj, uint64_t* cam_best, uint32_t* cam_dist,
+                                const uint32_t* fail, int32_t frame, const uint32_t* inst_gid, const void* proj, uint64_t* cam_best, uint32_t* cam_dist,
                                 const int32_t* mask, float* out_color, float* out_depth, float* out_invdepth,
                                 int32_t width, int32_t height, const float* background3_host, int32_t* work_counters,
                                 uint64_t* stats, void* stream) {
-    G2PC_CHECK_ARG(leaves && leaf_order && header && inst_gid && proj && cam_best && out_color && out_depth &&
+    G2PC_CHECK_ARG(leaves && leaf_order && header && fail && inst_gid && proj && cam_best && out_color && out_depth &&
                        out_invdepth && background3_host && work_counters, "null pointer");
     G2PC_CHECK_ARG(((uintptr_t)inst_gid & 15) == 0, "inst_gid must be 16-byte aligned (TMA bulk copies)");
     TileBlendParams p;
-    p.leaves = leaves; p.leaf_order = leaf_order; p.header = header; p.inst_gid = inst_gid;
+    p.leaves = leaves; p.leaf_order = leaf_order; p.header = header; p.fail = fail; p.frame = frame;
+    p.inst_gid = inst_gid;
     p.proj = (const float4*)proj; p.cam_best = (unsigned long long*)cam_best; p.cam_dist = cam_dist; p.mask = mask;
     p.out_color = out_color; p.out_depth = out_depth; p.out_invdepth = out_invdepth;
     p.W = width; p.H = height;

@@ -29,3 +29,7 @@ MAX_GAUSSIANS_PER_TILE = 60000
 # contributions that underflow are dropped (the strict-parity tests use it).  The reference's CUDA back-end stops each
 # pixel at T < 1e-4 (forward.cu:415); its python back-end never stops.
 BLEND_T_STOP = 1e-6
+
+# Frames (cameras) in flight in the colour stage: 2 = the front-end of camera f + 1 overlaps the blend of camera f on a
+# second CUDA stream (g2pc/frames.py); 1 = strictly serial.
+FRAME_SLOTS = 2

@@ -130,28 +130,27 @@ class GaussianRasterizer(FrameQueue):
         if shs is not None:
             self._shs_f32 = shs.to(torch.float32).contiguous()
             self._sh_stride = int(self._shs_f32.shape[2] if self._sh_layout == 0 else self._shs_f32.shape[1])
+        self._init_frames()
         m = max(n, 1)
-        self._proj = torch.empty((m, 12), dtype=torch.float32, device=dev)
+        nbytes = self.lib.g2pc_depth_sort_workspace_bytes(m)
+        self._slots = [dict(proj=torch.empty((m, 12), dtype=torch.float32, device=dev),
+                            depth_key=torch.empty((m,), dtype=torch.int32, device=dev),
+                            val=torch.empty((m,), dtype=torch.int64, device=dev),
+                            val_sorted=torch.empty((m,), dtype=torch.int64, device=dev),
+                            depth_ws=torch.empty((max(int(nbytes), 1),), dtype=torch.uint8, device=dev),
+                            hdr=torch.zeros((capi.HDR_WORDS,), dtype=torch.int32, device=dev),
+                            work=torch.zeros((capi.WORK_COUNTERS,), dtype=torch.int32, device=dev),
+                            radii=torch.zeros((m,), dtype=torch.int32, device=dev),
+                            inst_gid=None, matrix=None) for _ in range(self.num_slots)]
         self._cam_best = torch.zeros((m,), dtype=torch.int64, device=dev)
         self._cam_dist = None
         if calculate_surface_distance:
             self._cam_dist = torch.empty((m,), dtype=torch.int32, device=dev)
             capi.call("g2pc_fill_u32", capi.ptr(self._cam_dist), FLT_MAX_BITS, m, capi.stream_ptr(dev))
-        self._depth_key = torch.empty((m,), dtype=torch.int32, device=dev)
-        self._val = torch.empty((m,), dtype=torch.int64, device=dev)
-        self._val_sorted = torch.empty((m,), dtype=torch.int64, device=dev)
-        self._radii = torch.zeros((m,), dtype=torch.int32, device=dev)
-        nbytes = self.lib.g2pc_depth_sort_workspace_bytes(m)
-        self._depth_ws = torch.empty((max(int(nbytes), 1),), dtype=torch.uint8, device=dev)
-        self._hdr = torch.zeros((capi.HDR_WORDS,), dtype=torch.int32, device=dev)
-        self._work = torch.zeros((capi.WORK_COUNTERS,), dtype=torch.int32, device=dev)
         self._stats = torch.zeros((capi.STAT_WORDS,), dtype=torch.int64, device=dev)
-        self._inst_gid = None
-        self._matrix = None
         self._inst_cap = max(8 * n, 1 << 16)
         self._res = {}
-        self._ones_mask = None
-        self._init_frames()
+        self._last_slot = 0
         self.last_stats = {}
 
     # ---- nn.Module-like call surface -----------------------------------------------------------------------------------
@@ -180,76 +179,90 @@ class GaussianRasterizer(FrameQueue):
             if chunk <= 0:
                 raise capi.G2pcError(f"{ntiles} tiles: image too large for the multisplit tables")
             t = dict(gx=gx, gy=gy, ntiles=ntiles, rows=int(self.lib.g2pc_multisplit_rows(self._n, ntiles)),
-                     node_cnt=torch.zeros((ntiles,), dtype=torch.int32, device=dev),
-                     leaves=torch.zeros((ntiles, capi.LEAF_WORDS), dtype=torch.int32, device=dev),
-                     leaf_order=torch.zeros((ntiles,), dtype=torch.int32, device=dev),
+                     slots=[dict(node_cnt=torch.zeros((ntiles,), dtype=torch.int32, device=dev),
+                                 leaves=torch.zeros((ntiles, capi.LEAF_WORDS), dtype=torch.int32, device=dev),
+                                 leaf_order=torch.zeros((ntiles,), dtype=torch.int32, device=dev))
+                            for _ in range(self.num_slots)],
                      colour=torch.zeros((3, H, W), dtype=torch.float32, device=dev),
                      depth=torch.zeros((1, H, W), dtype=torch.float32, device=dev),
                      invdepth=torch.zeros((1, H, W), dtype=torch.float32, device=dev))
             self._res[(W, H)] = t
         return t
 
-    def _buffers(self, t):
+    def _buffers(self, t, sl):
         dev = self.device
         need = self._inst_cap + 4 * t["ntiles"] + 64
-        if self._inst_gid is None or self._inst_gid.numel() < need:
-            self._inst_gid = torch.empty((need,), dtype=torch.int32, device=dev)
+        if sl["inst_gid"] is None or sl["inst_gid"].numel() < need:
+            sl["inst_gid"] = torch.empty((need,), dtype=torch.int32, device=dev)
         mneed = t["rows"] * t["ntiles"]
-        if self._matrix is None or self._matrix.numel() < mneed:
-            self._matrix = torch.empty((max(mneed, 1),), dtype=torch.int32, device=dev)
+        if sl["matrix"] is None or sl["matrix"].numel() < mneed:
+            sl["matrix"] = torch.empty((max(mneed, 1),), dtype=torch.int32, device=dev)
 
-    def _enqueue(self, rs, frame, camera_index, per_camera=None):
+    def _mask_of(self, rs, W, H):
+        mask = rs.mask
+        if mask is None:
+            return None
+        if not mask.is_cuda:
+            raise capi.G2pcError("mask must be a CUDA tensor")
+        if mask.numel() != W * H:
+            raise capi.G2pcError("mask must have image_height * image_width entries")
+        return mask.to(torch.int32).contiguous()
+
+    def _enqueue_front(self, rs, frame, slot):
         st = capi.stream_ptr(self.device)
         W, H = int(rs.image_width), int(rs.image_height)
         n = self._n
         self._pack(float(rs.scale_modifier))
         t = self._res_tables(W, H)
-        self._buffers(t)
+        sl, ts = self._slots[slot], t["slots"][slot]
+        self._buffers(t, sl)
         c = _raster_struct(rs)
-        mask = rs.mask
-        if mask is not None:
-            if not mask.is_cuda:
-                raise capi.G2pcError("mask must be a CUDA tensor")
-            mask = mask.to(torch.int32).contiguous()
-            if mask.numel() != W * H:
-                raise capi.G2pcError("mask must have image_height * image_width entries")
+        deg = int(rs.sh_degree) if self._shs_f32 is not None else 0
+        capi.call("g2pc_tiles_preprocess", capi.ptr(self._geom), capi.ptr(self._colour_f32), capi.ptr(self._shs_f32),
+                  self._sh_stride if self._shs_f32 is not None else 0, min(deg, 3), self._sh_layout, n, ctypes.byref(c),
+                  capi.ptr(sl["proj"]), capi.ptr(ts["node_cnt"]), capi.ptr(sl["depth_key"]), capi.ptr(sl["val"]),
+                  capi.ptr(sl["radii"]), st)
+        capi.call("g2pc_depth_sort", capi.ptr(sl["depth_key"]), capi.ptr(sl["val"]), n, capi.ptr(sl["val_sorted"]),
+                  capi.ptr(sl["depth_ws"]), sl["depth_ws"].numel(), st)
+        capi.call("g2pc_tiles_build", capi.ptr(ts["node_cnt"]), W, H, capi.ptr(ts["leaves"]), capi.ptr(ts["leaf_order"]),
+                  t["ntiles"], self._inst_cap, sl["matrix"].numel(), t["rows"], frame, capi.ptr(sl["hdr"]),
+                  capi.ptr(self._fail), capi.ptr(sl["work"]), st)
+        capi.call("g2pc_multisplit_grid", capi.ptr(sl["val_sorted"]), n, t["gx"], t["gy"], capi.ptr(ts["leaves"]),
+                  capi.ptr(sl["hdr"]), capi.ptr(self._fail), frame, t["ntiles"], capi.ptr(sl["matrix"]),
+                  capi.ptr(sl["inst_gid"]), st)
+        self._last, self._last_slot = t, slot
+        return sl["hdr"]
+
+    def _enqueue_back(self, rs, frame, camera_index, slot):
+        st = capi.stream_ptr(self.device)
+        W, H = int(rs.image_width), int(rs.image_height)
+        n = self._n
+        t = self._res_tables(W, H)
+        sl, ts = self._slots[slot], t["slots"][slot]
+        mask = self._mask_of(rs, W, H)
         # pixels that are masked out are never written by the blend (forward.cu:485): they keep the zeros of the fresh
         # output tensors the reference allocates per call (rasterize_points.cu:72-90)
         if mask is not None:
             t["colour"].zero_(); t["depth"].zero_(); t["invdepth"].zero_()
         bg = (ctypes.c_float * 3)(*(getattr(rs, "_bg_host", None) or _host_list(rs.bg, 3)))
-        deg = int(rs.sh_degree) if self._shs_f32 is not None else 0
-        capi.call("g2pc_tiles_preprocess", capi.ptr(self._geom), capi.ptr(self._colour_f32), capi.ptr(self._shs_f32),
-                  self._sh_stride if self._shs_f32 is not None else 0, min(deg, 3), self._sh_layout, n, ctypes.byref(c),
-                  capi.ptr(self._proj), capi.ptr(t["node_cnt"]), capi.ptr(self._depth_key), capi.ptr(self._val),
-                  capi.ptr(self._radii), st)
-        capi.call("g2pc_depth_sort", capi.ptr(self._depth_key), capi.ptr(self._val), n, capi.ptr(self._val_sorted),
-                  capi.ptr(self._depth_ws), self._depth_ws.numel(), st)
-        capi.call("g2pc_tiles_build", capi.ptr(t["node_cnt"]), W, H, capi.ptr(t["leaves"]), capi.ptr(t["leaf_order"]),
-                  t["ntiles"], self._inst_cap, self._matrix.numel(), t["rows"], frame, capi.ptr(self._hdr),
-                  capi.ptr(self._work), st)
-        capi.call("g2pc_multisplit_grid", capi.ptr(self._val_sorted), n, t["gx"], t["gy"], capi.ptr(t["leaves"]),
-                  capi.ptr(self._hdr), t["ntiles"], capi.ptr(self._matrix), capi.ptr(self._inst_gid), st)
-        capi.call("g2pc_tiles_blend", capi.ptr(t["leaves"]), capi.ptr(t["leaf_order"]), capi.ptr(self._hdr),
-                  capi.ptr(self._inst_gid), capi.ptr(self._proj), capi.ptr(self._cam_best), capi.ptr(self._cam_dist),
-                  capi.ptr(mask), capi.ptr(t["colour"]), capi.ptr(t["depth"]), capi.ptr(t["invdepth"]), W, H, bg,
-                  capi.ptr(self._work), capi.ptr(self._stats), st)
-        pc = per_camera or (None, None, None)
+        capi.call("g2pc_tiles_blend", capi.ptr(ts["leaves"]), capi.ptr(ts["leaf_order"]), capi.ptr(sl["hdr"]),
+                  capi.ptr(self._fail), frame, capi.ptr(sl["inst_gid"]), capi.ptr(sl["proj"]), capi.ptr(self._cam_best),
+                  capi.ptr(self._cam_dist), capi.ptr(mask), capi.ptr(t["colour"]), capi.ptr(t["depth"]),
+                  capi.ptr(t["invdepth"]), W, H, bg, capi.ptr(sl["work"]), capi.ptr(self._stats), st)
+        pc = getattr(self, "_per_camera", None) or (None, None, None)
         capi.call("g2pc_tiles_accumulate", capi.ptr(self._cam_best), capi.ptr(self._cam_dist), capi.ptr(t["colour"]), W, H,
                   n, capi.ptr(self.gaussian_max_contribution), capi.ptr(self.gaussian_total_contribution),
                   capi.ptr(self.gaussian_colours), capi.ptr(self.gaussian_min_surface_distance),
                   capi.ptr(self.first_frame), int(camera_index), capi.ptr(pc[0]), capi.ptr(pc[1]), capi.ptr(pc[2]), st)
-        self._last = t
-        return t
 
     def forward(self, raster_settings, camera_index=None):
         """Render one camera and update the accumulators (__init__.py:90-140).
         Returns (colour (3,H,W), radii (P) int32, invdepths (1,H,W), depths (1,H,W))."""
         self._submit(raster_settings, camera_index)
-        t = self._last
-        if self.async_mode:  # shared buffers: final after flush(), overwritten by the next camera
-            return t["colour"], self._radii, t["invdepth"], t["depth"]
-        return t["colour"].clone(), self._radii.clone(), t["invdepth"].clone(), t["depth"].clone()
+        t, radii = self._last, self._slots[self._last_slot]["radii"]
+        if self.async_mode:  # shared buffers: final after flush(), overwritten by the next camera(s)
+            return t["colour"], radii, t["invdepth"], t["depth"]
+        return t["colour"].clone(), radii.clone(), t["invdepth"].clone(), t["depth"].clone()
 
     # ---- FrameQueue hooks ---------------------------------------------------------------------------------------------
     def _confirm(self, h):
@@ -263,9 +276,12 @@ class GaussianRasterizer(FrameQueue):
                 raise capi.G2pcError(f"{total} (Gaussian, tile) instances in one camera: more than 2^31 - 1")
             self._inst_cap = max(self._inst_cap, int(1.25 * total) + 1024)
         else:
-            raise capi.G2pcError("poisoned frame header without a recoverable cause")
+            raise capi.G2pcError("failed frame header without a recoverable cause")
+
+    def _reset_counts(self):
         for t in self._res.values():
-            t["node_cnt"].zero_()
+            for ts in t["slots"]:
+                ts["node_cnt"].zero_()
 
     def executed_pairs(self):
         """(pixel, Gaussian) pairs the blend evaluated since construction: 64 threads x 4 pixels per tile, 2 warps."""
@@ -351,15 +367,13 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     contrib = torch.zeros((n,), dtype=torch.float32, device=dev)
     pixels = torch.zeros((n,), dtype=torch.int32, device=dev)
     surf = torch.full((n,), torch.finfo(torch.float).max, dtype=torch.float32, device=dev)
-    frame = R._frame
-    R._frame += 1
-    R._enqueue(rs, frame, frame, per_camera=(contrib, pixels, surf if calculate_surface_distance else None))
-    R._record(frame, rs, frame)
+    R._per_camera = (contrib, pixels, surf if calculate_surface_distance else None)
+    R._submit(rs)
     R.flush()
     t = R._last
     empty = torch.empty((0,), dtype=torch.uint8, device=dev)
-    return (int(R.last_stats["total_instances"]), t["colour"], t["depth"], R._radii, empty, empty.clone(), empty.clone(),
-            t["invdepth"], contrib, surf, pixels)
+    return (int(R.last_stats["total_instances"]), t["colour"], t["depth"], R._slots[R._last_slot]["radii"], empty,
+            empty.clone(), empty.clone(), t["invdepth"], contrib, surf, pixels)
 
 
 def mark_visible(means3D, viewmatrix, projmatrix):

@@ -89,22 +89,23 @@ class GaussPythonRenderer(FrameQueue):
         self._geom = torch.empty((max(n, 1), 12), dtype=torch.float32, device=dev)
         capi.call("g2pc_pack_geometry", capi.ptr(self.means3D), capi.ptr(self.cov3d), capi.ptr(self.opacity), n,
                   capi.ptr(self._geom), st)
-        # per-camera scratch, allocated once
-        self._proj = torch.empty((max(n, 1), 12), dtype=torch.float32, device=dev)
-        self._cam_best = torch.zeros((max(n, 1),), dtype=torch.int64, device=dev)
-        self._depth_key = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
-        self._val = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
-        self._val_sorted = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
-        nbytes = self.lib.g2pc_depth_sort_workspace_bytes(max(n, 1))
-        self._depth_ws = torch.empty((max(int(nbytes), 1),), dtype=torch.uint8, device=dev)
-        self._hdr = torch.zeros((capi.HDR_WORDS,), dtype=torch.int32, device=dev)
-        self._work = torch.zeros((capi.WORK_COUNTERS,), dtype=torch.int32, device=dev)
-        self._stats = torch.zeros((capi.STAT_WORDS,), dtype=torch.int64, device=dev)
-        self._inst_gid = None
-        self._leaf_colour = None
-        self._matrix = None
-        self._inst_cap = max(8 * n, 1 << 16)
         self._init_frames()
+        # per-frame scratch: one set per slot (frames alternate between the slots)
+        m = max(n, 1)
+        nbytes = self.lib.g2pc_depth_sort_workspace_bytes(m)
+        self._slots = [dict(proj=torch.empty((m, 12), dtype=torch.float32, device=dev),
+                            depth_key=torch.empty((m,), dtype=torch.int32, device=dev),
+                            val=torch.empty((m,), dtype=torch.int64, device=dev),
+                            val_sorted=torch.empty((m,), dtype=torch.int64, device=dev),
+                            depth_ws=torch.empty((max(int(nbytes), 1),), dtype=torch.uint8, device=dev),
+                            hdr=torch.zeros((capi.HDR_WORDS,), dtype=torch.int32, device=dev),
+                            work=torch.zeros((capi.WORK_COUNTERS,), dtype=torch.int32, device=dev),
+                            inst_gid=None, matrix=None) for _ in range(self.num_slots)]
+        self._cam_best = torch.zeros((m,), dtype=torch.int64, device=dev)
+        self._stats = torch.zeros((capi.STAT_WORDS,), dtype=torch.int64, device=dev)
+        self._leaf_colour = None
+        self._inst_cap = max(8 * n, 1 << 16)
+        self._last_slot = 0
         self.last_stats = {}
 
     # ---- getters (gauss_render.py:237-264) -----------------------------------------------------------------
@@ -147,12 +148,13 @@ class GaussPythonRenderer(FrameQueue):
             if base > 8:
                 raise capi.G2pcError("image too large for the packed node range (first leaf level deeper than 8)")
             t = dict(qt=qt, tables=torch.from_numpy(flat).to(dev), level_mask=mask, base_level=base,
-                     node_cnt=torch.zeros((qt.nodes_2d,), dtype=torch.int32, device=dev),
-                     node_state=torch.zeros((qt.nodes_2d,), dtype=torch.uint8, device=dev),
-                     node_leaf=torch.full((qt.nodes_2d,), -1, dtype=torch.int32, device=dev),
+                     slots=[dict(node_cnt=torch.zeros((qt.nodes_2d,), dtype=torch.int32, device=dev),
+                                 node_state=torch.zeros((qt.nodes_2d,), dtype=torch.uint8, device=dev),
+                                 node_leaf=torch.full((qt.nodes_2d,), -1, dtype=torch.int32, device=dev),
+                                 leaves=None, leaf_order=None) for _ in range(self.num_slots)],
                      owner=torch.zeros((W * H,), dtype=torch.int32, device=dev),
                      image=torch.ones((H, W, 3), dtype=torch.float32, device=dev),
-                     leaf_cap=0, leaves=None, leaf_order=None, pix_cap=int(1.25 * W * H) + 4096,
+                     leaf_cap=0, pix_cap=int(1.25 * W * H) + 4096,
                      max_quads=int(((min(self.max_tile_size, W) + 3) // 4) * min(self.max_tile_size, H)))
             self._set_leaf_cap(t, min(qt.nodes_2d, 2 * (4 ** base)))
             self._tables[key] = t
@@ -165,8 +167,9 @@ class GaussPythonRenderer(FrameQueue):
             raise capi.G2pcError(f"the quadtree has more than {cap} leaves: too many for the multisplit tables")
         t["leaf_cap"], t["chunk"] = cap, chunk
         t["chunks"] = int(self.lib.g2pc_multisplit_rows(self._n, cap))  # matrix rows: chunks + persistent CTAs
-        t["leaves"] = torch.zeros((cap, capi.LEAF_WORDS), dtype=torch.int32, device=self.device)
-        t["leaf_order"] = torch.zeros((cap,), dtype=torch.int32, device=self.device)
+        for ts in t["slots"]:
+            ts["leaves"] = torch.zeros((cap, capi.LEAF_WORDS), dtype=torch.int32, device=self.device)
+            ts["leaf_order"] = torch.zeros((cap,), dtype=torch.int32, device=self.device)
 
     @staticmethod
     def _camera_struct(camera):
@@ -191,45 +194,56 @@ class GaussPythonRenderer(FrameQueue):
         c.height = camera.image_height
         return c
 
-    def _buffers(self, t):
-        """(Re)allocate the frame buffers for the current capacities."""
+    def _buffers(self, t, sl):
+        """(Re)allocate the slot's frame buffers for the current capacities."""
         dev = self.device
         need = self._inst_cap + 4 * t["leaf_cap"] + 64  # lists are padded to 16 bytes; slack for the last TMA unit
-        if self._inst_gid is None or self._inst_gid.numel() < need:
-            self._inst_gid = torch.empty((need,), dtype=torch.int32, device=dev)
+        if sl["inst_gid"] is None or sl["inst_gid"].numel() < need:
+            sl["inst_gid"] = torch.empty((need,), dtype=torch.int32, device=dev)
         if self._leaf_colour is None or self._leaf_colour.numel() < 3 * t["pix_cap"]:
             self._leaf_colour = torch.empty((3 * t["pix_cap"],), dtype=torch.float32, device=dev)
         mneed = t["chunks"] * t["leaf_cap"]
-        if self._matrix is None or self._matrix.numel() < mneed:
-            self._matrix = torch.empty((max(mneed, 1),), dtype=torch.int32, device=dev)
+        if sl["matrix"] is None or sl["matrix"].numel() < mneed:
+            sl["matrix"] = torch.empty((max(mneed, 1),), dtype=torch.int32, device=dev)
 
-    def _enqueue(self, camera, frame, camera_index):
-        """All kernels of one camera, asynchronously on the current stream."""
+    def _enqueue_front(self, camera, frame, slot):
+        """Projection, depth sort, tile table and per-tile lists of one camera, asynchronously on the current stream."""
         st = capi.stream_ptr(self.device)
         W, H = int(camera.image_width), int(camera.image_height)
         cam = self._camera_struct(camera)
         n = self._n
         t = self._get_tables(W, H)
         qt = t["qt"]
-        self._buffers(t)
-        bg = 1.0 if self.white_bkgd else 0.0
+        sl, ts = self._slots[slot], t["slots"][slot]
+        self._buffers(t, sl)
         capi.call("g2pc_preprocess", capi.ptr(self._geom), capi.ptr(self._colour_f32) if self.shs is None else None,
                   capi.ptr(self.shs), int(self.shs.shape[-1]) if self.shs is not None else 0, self.sh_degree, n,
-                  ctypes.byref(cam), capi.ptr(t["tables"]), qt.num_levels, t["level_mask"], capi.ptr(self._proj),
-                  capi.ptr(t["node_cnt"]), capi.ptr(self._depth_key), capi.ptr(self._val), st)
-        capi.call("g2pc_depth_sort", capi.ptr(self._depth_key), capi.ptr(self._val), n, capi.ptr(self._val_sorted),
-                  capi.ptr(self._depth_ws), self._depth_ws.numel(), st)
+                  ctypes.byref(cam), capi.ptr(t["tables"]), qt.num_levels, t["level_mask"], capi.ptr(sl["proj"]),
+                  capi.ptr(ts["node_cnt"]), capi.ptr(sl["depth_key"]), capi.ptr(sl["val"]), st)
+        capi.call("g2pc_depth_sort", capi.ptr(sl["depth_key"]), capi.ptr(sl["val"]), n, capi.ptr(sl["val_sorted"]),
+                  capi.ptr(sl["depth_ws"]), sl["depth_ws"].numel(), st)
         capi.call("g2pc_build_tree", capi.ptr(t["tables"]), qt.num_levels, qt.max_gaussians_per_tile,
-                  capi.ptr(t["node_cnt"]), capi.ptr(t["node_state"]), capi.ptr(t["node_leaf"]), capi.ptr(t["leaves"]),
-                  capi.ptr(t["leaf_order"]), t["leaf_cap"], self._inst_cap, t["pix_cap"], self._matrix.numel(),
-                  t["chunks"], frame, capi.ptr(self._hdr), capi.ptr(self._work), st)
-        capi.call("g2pc_multisplit", capi.ptr(self._val_sorted), n, capi.ptr(self._proj), W, H, capi.ptr(t["tables"]),
-                  qt.num_levels, t["level_mask"], capi.ptr(t["node_leaf"]), capi.ptr(t["leaves"]), capi.ptr(self._hdr),
-                  t["leaf_cap"], capi.ptr(self._matrix), capi.ptr(self._inst_gid), st)
-        capi.call("g2pc_blend", capi.ptr(t["leaves"]), capi.ptr(t["leaf_order"]), capi.ptr(self._hdr), t["max_quads"],
-                  capi.ptr(self._inst_gid), capi.ptr(self._proj), capi.ptr(self._cam_best),
-                  capi.ptr(self.gaussian_max_contribution), capi.ptr(self._leaf_colour), capi.ptr(t["owner"]), W, H, bg,
-                  float(self.t_stop), capi.ptr(self._work), capi.ptr(self._stats), st)
+                  capi.ptr(ts["node_cnt"]), capi.ptr(ts["node_state"]), capi.ptr(ts["node_leaf"]), capi.ptr(ts["leaves"]),
+                  capi.ptr(ts["leaf_order"]), t["leaf_cap"], self._inst_cap, t["pix_cap"], sl["matrix"].numel(),
+                  t["chunks"], frame, capi.ptr(sl["hdr"]), capi.ptr(self._fail), capi.ptr(sl["work"]), st)
+        capi.call("g2pc_multisplit", capi.ptr(sl["val_sorted"]), n, capi.ptr(sl["proj"]), W, H, capi.ptr(t["tables"]),
+                  qt.num_levels, t["level_mask"], capi.ptr(ts["node_leaf"]), capi.ptr(ts["leaves"]), capi.ptr(sl["hdr"]),
+                  capi.ptr(self._fail), frame, t["leaf_cap"], capi.ptr(sl["matrix"]), capi.ptr(sl["inst_gid"]), st)
+        self._last_tables, self._last_slot = t, slot
+        return sl["hdr"]
+
+    def _enqueue_back(self, camera, frame, camera_index, slot):
+        """Blend + accumulator update (+ image) of one camera; runs after the previous camera's accumulator update."""
+        st = capi.stream_ptr(self.device)
+        W, H = int(camera.image_width), int(camera.image_height)
+        n = self._n
+        t = self._get_tables(W, H)
+        sl, ts = self._slots[slot], t["slots"][slot]
+        bg = 1.0 if self.white_bkgd else 0.0
+        capi.call("g2pc_blend", capi.ptr(ts["leaves"]), capi.ptr(ts["leaf_order"]), capi.ptr(sl["hdr"]),
+                  capi.ptr(self._fail), frame, t["max_quads"], capi.ptr(sl["inst_gid"]), capi.ptr(sl["proj"]),
+                  capi.ptr(self._cam_best), capi.ptr(self.gaussian_max_contribution), capi.ptr(self._leaf_colour),
+                  capi.ptr(t["owner"]), W, H, bg, float(self.t_stop), capi.ptr(sl["work"]), capi.ptr(self._stats), st)
         capi.call("g2pc_accumulate", capi.ptr(self._cam_best), capi.ptr(self._leaf_colour), n,
                   capi.ptr(self.gaussian_max_contribution), capi.ptr(self.gaussian_colours),
                   capi.ptr(self.first_frame), int(camera_index), st)
@@ -238,8 +252,6 @@ class GaussPythonRenderer(FrameQueue):
                       capi.ptr(t["image"]), st)
         else:
             t["owner"].zero_()
-        self._last_tables = t
-        return t
 
     def __call__(self, camera, camera_index=None, **kwargs):
         """Render one camera and update the per-Gaussian accumulators (gauss_render.py:404-465).
@@ -284,21 +296,24 @@ class GaussPythonRenderer(FrameQueue):
             t["pix_cap"] = max(t["pix_cap"], int(1.25 * h[capi.HDR_TOTAL_PIX]) + 1024)
         else:
             raise capi.G2pcError("poisoned frame header without a cause")
+
+    def _reset_counts(self):
         for tt in self._tables.values():
-            tt["node_cnt"].zero_()
+            for ts in tt["slots"]:
+                ts["node_cnt"].zero_()
 
     # ---- introspection for the parity tests ---------------------------------------------------------------------
     def debug_last_camera(self):
         """Per-Gaussian projection records and per-leaf sorted Gaussian ids of the most recent camera (host copies)."""
         self.flush()
-        t = self._last_tables
+        t, sl = self._last_tables, self._slots[self._last_slot]
         nl = self.last_stats["num_leaves"]
-        leaves = t["leaves"][:nl].cpu().numpy()
-        gids = self._inst_gid.cpu().numpy().astype(np.int64) if nl else np.zeros(0, np.int64)
+        leaves = t["slots"][self._last_slot]["leaves"][:nl].cpu().numpy()
+        gids = sl["inst_gid"].cpu().numpy().astype(np.int64) if nl else np.zeros(0, np.int64)
         out = []
         for (r0, c0, w, h, beg, cnt, pix, node) in leaves:
             out.append((int(r0), int(c0), int(w), int(h), gids[beg:beg + cnt]))
-        return self._proj.cpu().numpy(), out
+        return sl["proj"].cpu().numpy(), out
 
 
 def get_renderer(renderer_type: str, xyz, opacities, colours, covariances, shs=None, visible_gaussian_threshold=0.0,

@@ -158,9 +158,8 @@ typedef struct {
 #define G2PC_HDR_NEED_DEEPER 3    /* a tile at the deepest tabulated level still has to split: tabulate more levels */
 #define G2PC_HDR_LEAF_OVERFLOW 4  /* more leaves than max_leaves */
 #define G2PC_HDR_CAP_OVERFLOW 5   /* instance / leaf-pixel / multisplit-matrix capacity too small for this frame */
-#define G2PC_HDR_POISON 6         /* sticky: 1 + frame number of the first frame that failed; while non-zero
-                                     build_tree, multisplit, blend and accumulate do nothing (the caller clears the
-                                     word after growing its buffers and replays from that frame) */
+#define G2PC_HDR_POISON 6         /* snapshot of the shared failure word at the end of this frame's build_tree: 0 = no
+                                     frame has failed, else 1 + the LOWEST frame number that did not fit */
 #define G2PC_HDR_FRAME 7          /* frame number of the header's contents */
 #define G2PC_HDR_TOTAL_INST_HI 8
 #define G2PC_HDR_WORDS 16
@@ -168,6 +167,12 @@ typedef struct {
 /* device-side statistics (uint64 words, accumulated by g2pc_blend when `stats` is not NULL) */
 #define G2PC_STAT_WARP_GAUSSIANS 0  /* (warp, Gaussian) iterations executed: x 128 = (pixel, Gaussian) pairs */
 #define G2PC_STAT_WORDS 4
+
+/* The failure word `fail` (one uint32 in device memory, shared by the frames in flight, initialised to 0xFFFFFFFF):
+ * build_tree lowers it to 1 + frame when the frame does not fit; build_tree, multisplit and blend of frame f do nothing
+ * iff f + 1 >= *fail.  Frames may be enqueued on two streams (the front-end of frame f + 1 overlaps the blend of frame
+ * f), so a later frame can fail first: earlier frames still complete.  The caller resets the word after growing its
+ * buffers and replays from the failed frame. */
 
 /* Quadtree tables (host-built, g2pc/quadtree.py): `tables` = 6 int32 arrays of n1 = 2^num_levels - 1 entries each,
  * concatenated: x start, x end (inclusive), x flags, y start, y end, y flags; level l at offset 2^l - 1.
@@ -204,7 +209,8 @@ int g2pc_depth_sort(const uint32_t* depth_key, const uint64_t* val, int64_t n, u
 int g2pc_build_tree(const int32_t* tables, int32_t num_levels, int32_t max_gaussians_per_tile, uint32_t* node_cnt,
                     uint8_t* node_state, int32_t* node_leaf, g2pc_leaf_t* leaves, int32_t* leaf_order,
                     int32_t max_leaves, int64_t inst_capacity, int64_t pix_capacity, int64_t matrix_capacity,
-                    int32_t ms_chunks, int32_t frame, int32_t* header, int32_t* work_counters, void* stream);
+                    int32_t ms_chunks, int32_t frame, int32_t* header, uint32_t* fail, int32_t* work_counters,
+                    void* stream);
 
 /* S4c.  Stable multisplit of the depth-ordered stream into the leaves' lists: inst_gid[leaf.inst_begin ..
  * + leaf.inst_count) = Gaussian ids overlapping the leaf, nearest first.  Three kernels (count, scan, scatter) over
@@ -215,8 +221,8 @@ int32_t g2pc_multisplit_chunk(int32_t leaf_cap);
 int32_t g2pc_multisplit_rows(int64_t n, int32_t leaf_cap); /* rows of `matrix` needed (chunks + one per persistent CTA) */
 int g2pc_multisplit(const uint64_t* val_sorted, int64_t n, const void* proj, int32_t width, int32_t height,
                     const int32_t* tables, int32_t num_levels, uint32_t level_mask, const int32_t* node_leaf,
-                    const g2pc_leaf_t* leaves, const int32_t* header, int32_t leaf_cap, uint32_t* matrix,
-                    uint32_t* inst_gid, void* stream);
+                    const g2pc_leaf_t* leaves, const int32_t* header, const uint32_t* fail, int32_t frame,
+                    int32_t leaf_cap, uint32_t* matrix, uint32_t* inst_gid, void* stream);
 
 /* S5.  Front-to-back blend of every leaf (gauss_render.py:337-369) + per-Gaussian maximum contribution / arg-max pixel
  * (:371-385) published as cam_best[g] = max((bits(contribution) << 32) | ~leaf_pixel_index).
@@ -229,8 +235,8 @@ int g2pc_multisplit(const uint64_t* val_sorted, int64_t n, const void* proj, int
  * contribution it skips is then < t_stop and their sum per pixel is < t_stop.  t_stop = 0 selects FLT_MIN (only
  * contributions that underflow are dropped: the strict-parity setting); the reference's CUDA back-end stops each pixel
  * at T < 1e-4 (forward.cu:415).  stats: G2PC_STAT_WORDS uint64 or NULL. */
-int g2pc_blend(const g2pc_leaf_t* leaves, const int32_t* leaf_order, const int32_t* header,
-               int32_t max_leaf_pixels_quads, const uint32_t* inst_gid, const void* proj, uint64_t* cam_best,
+int g2pc_blend(const g2pc_leaf_t* leaves, const int32_t* leaf_order, const int32_t* header, const uint32_t* fail,
+               int32_t frame, int32_t max_leaf_pixels_quads, const uint32_t* inst_gid, const void* proj, uint64_t* cam_best,
                const float* max_contrib, float* leaf_colour, uint32_t* owner, int32_t width, int32_t height,
                float background, float t_stop, int32_t* work_counters, uint64_t* stats, void* stream);
 
@@ -273,20 +279,20 @@ int g2pc_tiles_preprocess(const void* geom, const float* colours, const float* s
  * offsets, launch order, frame header / poison as g2pc_build_tree; clears node_cnt and work_counters. */
 int g2pc_tiles_build(uint32_t* node_cnt, int32_t width, int32_t height, g2pc_leaf_t* leaves, int32_t* leaf_order,
                      int32_t max_leaves, int64_t inst_capacity, int64_t matrix_capacity, int32_t ms_rows, int32_t frame,
-                     int32_t* header, int32_t* work_counters, void* stream);
+                     int32_t* header, uint32_t* fail, int32_t* work_counters, void* stream);
 
 /* g2pc_multisplit over the tile grid (the packed range is the tile rect). */
 int g2pc_multisplit_grid(const uint64_t* val_sorted, int64_t n, int32_t grid_w, int32_t grid_h,
-                         const g2pc_leaf_t* leaves, const int32_t* header, int32_t leaf_cap, uint32_t* matrix,
-                         uint32_t* inst_gid, void* stream);
+                         const g2pc_leaf_t* leaves, const int32_t* header, const uint32_t* fail, int32_t frame,
+                         int32_t leaf_cap, uint32_t* matrix, uint32_t* inst_gid, void* stream);
 
 /* renderCUDA: per pixel front-to-back blend (power > 0 and alpha < 1/255 skipped, the pixel stops before T < 1e-4),
  * out_color (3,H,W) = C + T*bg, out_depth / out_invdepth (H,W) = sum depth*alpha*T / sum alpha*T/depth, written for
  * pixels inside the image whose mask (H*W int32 or NULL) is non-zero; cam_best[g] = max((bits(alpha*T) << 32) |
  * ~pixel_id) (deterministic arg-max: lowest pixel id among equals); cam_dist (n uint32, pre-filled with the bits of
  * FLT_MAX, or NULL): bits of the minimum surface distance (see s7_tiles.cu header). */
-int g2pc_tiles_blend(const g2pc_leaf_t* leaves, const int32_t* leaf_order, const int32_t* header,
-                     const uint32_t* inst_gid, const void* proj, uint64_t* cam_best, uint32_t* cam_dist,
+int g2pc_tiles_blend(const g2pc_leaf_t* leaves, const int32_t* leaf_order, const int32_t* header, const uint32_t* fail,
+                     int32_t frame, const uint32_t* inst_gid, const void* proj, uint64_t* cam_best, uint32_t* cam_dist,
                      const int32_t* mask, float* out_color, float* out_depth, float* out_invdepth, int32_t width,
                      int32_t height, const float* background3_host, int32_t* work_counters, uint64_t* stats,
                      void* stream);
