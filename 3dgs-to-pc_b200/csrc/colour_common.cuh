@@ -103,17 +103,19 @@ __device__ __forceinline__ bool axis_member(const int32_t* __restrict__ s, const
     return !(f[i] & QT_FLAG_DROPPED) && e[i] > s[i];
 }
 
-// Warp-cooperative walk over per-lane node rectangles.  Every lane brings a rectangle [xlo..xhi] x [ylo..yhi] (empty if
-// xlo > xhi) and a 32-bit payload; f(ix, iy, owner_lane, owner_payload) is called once per (lane, node).  Rectangles of
-// up to WARP_SMALL_AREA nodes are walked by their own lane; larger ones (a few huge splats cover hundreds of tiles) are
-// walked by the whole warp, 32 nodes at a time — without this the warp runs at the speed of its largest rectangle
-// (ncu r02a: 6.9 of 32 threads active in the multisplit).  Must be called by all 32 lanes.
-constexpr int WARP_SMALL_AREA = 6;
+// Warp-cooperative walk over per-lane node rectangles.  Every lane brings a packed rectangle (g2pc_pack_range; empty if
+// xlo > xhi) and a 32-bit payload; f(ix, iy, owner_lane, owner_payload) is called once per (lane, node).  Rectangles of up
+// to WARP_SMALL_AREA nodes are walked by their own lane; larger ones (a few huge splats cover hundreds of tiles) are
+// walked by the whole warp — the lanes tile the rectangle with a power-of-two number of columns, so no division is
+// needed — otherwise the warp runs at the speed of its largest rectangle (ncu r02a: 6.9 of 32 threads active in the
+// multisplit).  Must be called by all 32 lanes.
+constexpr int WARP_SMALL_AREA = 4;
 template <typename F>
-__device__ __forceinline__ void warp_for_each_node(int xlo, int xhi, int ylo, int yhi, uint32_t payload, F f) {
+__device__ __forceinline__ void warp_for_each_node(uint32_t range, uint32_t payload, F f) {
     const int lane = threadIdx.x & 31;
-    const int w = xhi - xlo + 1;
-    const int area = (xlo > xhi || ylo > yhi) ? 0 : w * (yhi - ylo + 1);
+    int xlo, xhi, ylo, yhi;
+    g2pc_unpack_range(range, xlo, xhi, ylo, yhi);
+    const int area = (xlo > xhi || ylo > yhi) ? 0 : (xhi - xlo + 1) * (yhi - ylo + 1);
     if (area > 0 && area <= WARP_SMALL_AREA)
         for (int iy = ylo; iy <= yhi; ++iy)
             for (int ix = xlo; ix <= xhi; ++ix) f(ix, iy, lane, payload);
@@ -121,12 +123,19 @@ __device__ __forceinline__ void warp_for_each_node(int xlo, int xhi, int ylo, in
     while (big) {
         const int b = __ffs(big) - 1;
         big &= big - 1u;
-        const int bx = __shfl_sync(0xffffffffu, xlo, b), by = __shfl_sync(0xffffffffu, ylo, b);
-        const int bw = __shfl_sync(0xffffffffu, w, b), ba = __shfl_sync(0xffffffffu, area, b);
+        const uint32_t br = __shfl_sync(0xffffffffu, range, b);
         const uint32_t bp = __shfl_sync(0xffffffffu, payload, b);
-        for (int t = lane; t < ba; t += 32) {
-            const int ry = t / bw;
-            f(bx + (t - ry * bw), by + ry, b, bp);
+        int bx, bxh, by, byh;
+        g2pc_unpack_range(br, bx, bxh, by, byh);
+        const int bw = bxh - bx + 1, bh = byh - by + 1;
+        const int sh = bw <= 1 ? 0 : 32 - __clz(bw - 1);  // ceil(log2(width))
+        if (sh >= 5) {
+            for (int ry = 0; ry < bh; ++ry)
+                for (int rx = lane; rx < bw; rx += 32) f(bx + rx, by + ry, b, bp);
+        } else {
+            const int rx = lane & ((1 << sh) - 1);
+            if (rx < bw)
+                for (int ry = lane >> sh; ry < bh; ry += 32 >> sh) f(bx + rx, by + ry, b, bp);
         }
     }
 }

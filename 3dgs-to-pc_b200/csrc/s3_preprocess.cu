@@ -29,6 +29,7 @@ struct PreParams {
     g2pc_camera_t cam;
     QtMeta meta;
     QtTables tab;
+    const uint16_t* luts;  // per level [x lo (W)][x hi+1 (W)][y lo (H)][y hi+1 (H)] (g2pc/quadtree.py pixel_luts)
     int32_t n1;  // entries per 1-D table array
     float4* proj;
     uint32_t* node_cnt;
@@ -37,6 +38,7 @@ struct PreParams {
     int32_t nodes_2d;     // histogram entries (0: no shared-memory histogram, global atomics)
     int32_t hist_off;     // first 2-D node of the shared-memory histogram (= off2(base level))
     uint32_t level_mask;  // bit l: level l has leaf-candidate nodes
+    uint32_t clean_mask;  // bit l: level l has no dropped / degenerate node (membership = the looked-up range)
     int32_t base_level;   // lowest set bit of level_mask
 };
 
@@ -95,6 +97,16 @@ __global__ void __launch_bounds__(256, 4) preprocess_kernel(const PreParams p) {
     extern __shared__ int32_t smem_tab[];
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_tab + 6 * p.n1);
     for (int k = threadIdx.x; k < p.nodes_2d; k += blockDim.x) s_hist[k] = 0u;
+    // pixel -> node-range lookups of every level (replace the per-Gaussian interval walks: ~80 % of this kernel's
+    // instructions in the r02a capture)
+    uint16_t* s_lut = reinterpret_cast<uint16_t*>(s_hist + p.nodes_2d);
+    const int lut_level = 2 * (p.cam.width + p.cam.height);
+    {
+        const int words = (lut_level * p.meta.num_levels + 1) / 2;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.luts);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_lut);
+        for (int k = threadIdx.x; k < words; k += blockDim.x) dst[k] = src[k];
+    }
     const QtTables T = load_tables(p.tab, p.n1, smem_tab);  // ends with __syncthreads()
     const bool use_hist = p.nodes_2d > 0;
     const int64_t cta_base = (int64_t)blockIdx.x * PRE_PER_CTA;
@@ -190,34 +202,43 @@ __global__ void __launch_bounds__(256, 4) preprocess_kernel(const PreParams p) {
         has_rect = true;
     }
     // ---- quadtree membership (all 32 lanes: the base-level walk is warp-cooperative) ----------------------------------
-    const float isx0 = 1.0f / (float)p.cam.width, isy0 = 1.0f / (float)p.cam.height;
+    // the rect lies in [0, W-1] x [0, H-1]: lo = first node with end > floor(min), hi = last node with start < ceil(max)
+    const int qx0 = (int)x0, qy0 = (int)y0, cx1 = (int)ceilf(x1), cy1 = (int)ceilf(y1);
     int bxlo = 1, bxhi = 0, bylo = 1, byhi = 0;
     {
         const int l = p.base_level;
         const int o1 = (1 << l) - 1;
-        if (has_rect) {
-            axis_range(T.xs + o1, T.xe + o1, l, x0, x1, isx0 * (float)(1 << l), bxlo, bxhi);
-            axis_range(T.ys + o1, T.ye + o1, l, y0, y1, isy0 * (float)(1 << l), bylo, byhi);
+        if (has_rect && x1 > x0 && y1 > y0) {
+            const uint16_t* L = s_lut + l * lut_level;
+            bxlo = L[qx0]; bxhi = (int)L[p.cam.width + cx1] - 1;
+            bylo = L[2 * p.cam.width + qy0]; byhi = (int)L[2 * p.cam.width + p.cam.height + cy1] - 1;
             if (bxlo > bxhi || bylo > byhi) { bxlo = 1; bxhi = 0; bylo = 1; byhi = 0; }
             else range = g2pc_pack_range(bxlo, bxhi, bylo, byhi);
         }
         uint32_t* cnt = p.node_cnt + off2(l);
-        warp_for_each_node(bxlo, bxhi, bylo, byhi, 0u, [&](int ix, int iy, int, uint32_t) {
-            if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy) || !axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) return;
-            if (use_hist) atomicAdd(s_hist + off2(l) + (iy << l) + ix, 1u);
-            else atomicAdd(cnt + (iy << l) + ix, 1u);
-        });
+        uint32_t* hcnt = s_hist + off2(l);
+        if ((p.clean_mask >> l) & 1u) {
+            warp_for_each_node(range, 0u, [&](int ix, int iy, int, uint32_t) {
+                if (use_hist) atomicAdd(hcnt + (iy << l) + ix, 1u);
+                else atomicAdd(cnt + (iy << l) + ix, 1u);
+            });
+        } else {
+            warp_for_each_node(range, 0u, [&](int ix, int iy, int, uint32_t) {
+                if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy) || !axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) return;
+                if (use_hist) atomicAdd(hcnt + (iy << l) + ix, 1u);
+                else atomicAdd(cnt + (iy << l) + ix, 1u);
+            });
+        }
     }
     if (has_rect && bxlo <= bxhi) {
         // deeper candidate levels exist only after a count-driven split asked for them (rare): per lane
         for (int l = p.base_level + 1; l < p.meta.num_levels; ++l) {
             if (!((p.level_mask >> l) & 1u)) continue;
             const int o1 = (1 << l) - 1;
-            int xlo, xhi, ylo, yhi;
-            axis_range(T.xs + o1, T.xe + o1, l, x0, x1, isx0 * (float)(1 << l), xlo, xhi);
-            if (xlo > xhi) continue;
-            axis_range(T.ys + o1, T.ye + o1, l, y0, y1, isy0 * (float)(1 << l), ylo, yhi);
-            if (ylo > yhi) continue;
+            const uint16_t* L = s_lut + l * lut_level;
+            const int xlo = L[qx0], xhi = (int)L[p.cam.width + cx1] - 1;
+            const int ylo = L[2 * p.cam.width + qy0], yhi = (int)L[2 * p.cam.width + p.cam.height + cy1] - 1;
+            if (xlo > xhi || ylo > yhi) continue;
             uint32_t* cnt = p.node_cnt + off2(l);
             for (int iy = ylo; iy <= yhi; ++iy) {
                 if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy)) continue;
@@ -230,22 +251,25 @@ __global__ void __launch_bounds__(256, 4) preprocess_kernel(const PreParams p) {
         }
         // levels above: every node splits by its size, only "is anything in it" matters (an empty tile is background
         // and has no children, gauss_render.py:313-315).  A child tile may overhang its parent by a pixel, so this is
-        // NOT implied by the leaf-level counts: walk up from the base range (the exact range at level l starts within
-        // one node of the halved range of level l + 1) and raise plain flags — no atomics.
-        int gxlo = bxlo, gxhi = bxhi, gylo = bylo, gyhi = byhi;
+        // NOT implied by the leaf-level counts: look the exact range of every level up and raise plain flags.
         for (int l = p.base_level - 1; l >= 0; --l) {
             const int o1 = (1 << l) - 1;
-            int xlo, xhi, ylo, yhi;
-            axis_range_from(T.xs + o1, T.xe + o1, l, x0, x1, gxlo >> 1, gxhi >> 1, xlo, xhi);
-            axis_range_from(T.ys + o1, T.ye + o1, l, y0, y1, gylo >> 1, gyhi >> 1, ylo, yhi);
-            gxlo = xlo; gxhi = xhi; gylo = ylo; gyhi = yhi;
+            const uint16_t* L = s_lut + l * lut_level;
+            const int xlo = L[qx0], xhi = (int)L[p.cam.width + cx1] - 1;
+            const int ylo = L[2 * p.cam.width + qy0], yhi = (int)L[2 * p.cam.width + p.cam.height + cy1] - 1;
             if (xlo > xhi || ylo > yhi) continue;
+            uint32_t* flags = (use_hist ? s_hist : p.node_cnt) + off2(l);
+            if ((p.clean_mask >> l) & 1u) {
+                // (almost always a single node)
+                for (int iy = ylo; iy <= yhi; ++iy)
+                    for (int ix = xlo; ix <= xhi; ++ix) flags[(iy << l) + ix] = 1u;
+                continue;
+            }
             for (int iy = ylo; iy <= yhi; ++iy) {
                 if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy)) continue;
                 for (int ix = xlo; ix <= xhi; ++ix) {
                     if (!axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) continue;
-                    if (use_hist) s_hist[off2(l) + (iy << l) + ix] = 1u;
-                    else p.node_cnt[off2(l) + (iy << l) + ix] = 1u;
+                    flags[(iy << l) + ix] = 1u;
                 }
             }
         }
@@ -302,11 +326,13 @@ extern "C" int g2pc_pack_geometry(const float* xyz, const float* cov, const floa
 
 extern "C" int g2pc_preprocess(const void* geom, const float* colours, const float* shs, int32_t sh_stride,
                                int32_t sh_degree, int64_t n, const g2pc_camera_t* cam_host, const int32_t* tables,
-                               int32_t num_levels, uint32_t level_mask, void* proj, uint32_t* node_cnt,
-                               uint32_t* depth_key, uint64_t* val, void* stream) {
+                               const uint16_t* luts, int32_t num_levels, uint32_t level_mask, uint32_t clean_mask,
+                               void* proj,
+                               uint32_t* node_cnt, uint32_t* depth_key, uint64_t* val, void* stream) {
     G2PC_CHECK_ARG(n >= 0, "n < 0");
     if (n == 0) return G2PC_OK;
-    G2PC_CHECK_ARG(geom && cam_host && tables && proj && node_cnt && depth_key && val, "null pointer");
+    G2PC_CHECK_ARG(geom && cam_host && tables && luts && proj && node_cnt && depth_key && val, "null pointer");
+    G2PC_CHECK_ARG(((uintptr_t)luts & 3) == 0, "luts must be 4-byte aligned");
     G2PC_CHECK_ARG(n <= 0xFFFFFFFFll, "more than 2^32 Gaussians");
     G2PC_CHECK_ARG((colours != nullptr) != (shs != nullptr), "provide exactly one of colours / shs");
     G2PC_CHECK_ARG(num_levels >= 1 && num_levels <= G2PC_MAX_LEVELS, "bad num_levels");
@@ -320,14 +346,18 @@ extern "C" int g2pc_preprocess(const void* geom, const float* colours, const flo
     p.meta.width = cam_host->width; p.meta.height = cam_host->height;
     p.n1 = (1 << num_levels) - 1;
     p.tab = make_tables(tables, p.n1);
+    p.luts = luts;
     p.proj = (float4*)proj; p.node_cnt = node_cnt; p.depth_key = depth_key; p.val = (unsigned long long*)val;
     p.level_mask = level_mask;
+    p.clean_mask = clean_mask;
     p.base_level = __builtin_ctz(level_mask);
     G2PC_CHECK_ARG(p.base_level <= G2PC_RANGE_MAX_LEVEL, "first leaf-candidate level too deep for the packed node range");
     const int nodes_all = ((1 << (2 * num_levels)) - 1) / 3;
     p.hist_off = 0;
     p.nodes_2d = nodes_all <= 24 * 1024 ? nodes_all : 0;  // histogram in shared memory when it fits (<= 96 KB)
-    const size_t smem = (size_t)6 * p.n1 * sizeof(int32_t) + (size_t)p.nodes_2d * sizeof(uint32_t);
+    const size_t lut_bytes = ((size_t)2 * (cam_host->width + cam_host->height) * num_levels * sizeof(uint16_t) + 3) & ~(size_t)3;
+    const size_t smem = (size_t)6 * p.n1 * sizeof(int32_t) + (size_t)p.nodes_2d * sizeof(uint32_t) + lut_bytes;
+    G2PC_CHECK_ARG(smem <= 220 * 1024, "quadtree tables do not fit the shared memory of one SM");
     if (smem > 48 * 1024)
         G2PC_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     preprocess_kernel<<<(unsigned)((n + PRE_PER_CTA - 1) / PRE_PER_CTA), 256, smem, (cudaStream_t)stream>>>(p);

@@ -263,6 +263,7 @@ struct MsParams {
     uint32_t* matrix;      // [chunk][num_leaves]: counts, then absolute list offsets (in place)
     uint32_t* inst_gid;
     int32_t leaf_cap;      // leaves the shared-memory tables are sized for (<= max_leaves of the tree)
+    int32_t base_clean;    // the base level has no dropped / degenerate node: membership = the packed range, no table look-ups
     int32_t grid_w;        // > 0: flat tile grid (s7_tiles.cu): leaf = iy * grid_w + ix, the packed range is the tile rect
 };
 
@@ -270,23 +271,30 @@ struct MsParams {
 template <typename F>
 __device__ __forceinline__ void for_each_leaf(const MsParams& p, const QtTables& T, const int32_t* __restrict__ s_leaf,
                                               uint32_t range, uint32_t gid, F f) {
-    int xlo, xhi, ylo, yhi;
-    g2pc_unpack_range(range, xlo, xhi, ylo, yhi);
     if (p.grid_w > 0) {
-        warp_for_each_node(xlo, xhi, ylo, yhi, gid,
-                           [&](int ix, int iy, int owner, uint32_t og) { f(iy * p.grid_w + ix, owner, og); });
+        warp_for_each_node(range, gid, [&](int ix, int iy, int owner, uint32_t og) { f(iy * p.grid_w + ix, owner, og); });
         return;
     }
     const int lb = p.base_level;
     const int o1 = (1 << lb) - 1;
     unsigned deeper = 0;
-    warp_for_each_node(xlo, xhi, ylo, yhi, gid, [&](int ix, int iy, int owner, uint32_t og) {
-        if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy) || !axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) return;
-        const int32_t v = s_leaf[(iy << lb) + ix];
-        if (v >= 0) f(v, owner, og);
-        else if (v == -2) deeper |= 1u << owner;
-    });
+    if (p.base_clean) {
+        warp_for_each_node(range, gid, [&](int ix, int iy, int owner, uint32_t og) {
+            const int32_t v = s_leaf[(iy << lb) + ix];
+            if (v >= 0) f(v, owner, og);
+            else if (v == -2) deeper |= 1u << owner;
+        });
+    } else {
+        warp_for_each_node(range, gid, [&](int ix, int iy, int owner, uint32_t og) {
+            if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy) || !axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) return;
+            const int32_t v = s_leaf[(iy << lb) + ix];
+            if (v >= 0) f(v, owner, og);
+            else if (v == -2) deeper |= 1u << owner;
+        });
+    }
     if (p.meta.num_levels <= lb + 1) return;
+    int xlo, xhi, ylo, yhi;
+    g2pc_unpack_range(range, xlo, xhi, ylo, yhi);
     // ---- count-driven splits below the base level (rare): per lane ----
     // combine the flags raised on behalf of each owner
 #pragma unroll
@@ -330,7 +338,12 @@ __device__ __forceinline__ void for_each_leaf(const MsParams& p, const QtTables&
 // shared memory of the count / scatter kernels: [6 * n1 table ints][4^base node->leaf ints][payload]
 __device__ __forceinline__ int32_t* ms_load_common(const MsParams& p, int32_t* smem, QtTables& T) {
     if (p.grid_w > 0) { T = p.tab; return smem; }  // tile grid: nothing to stage
-    T = load_tables(p.tab, p.n1, smem);  // ends with __syncthreads()
+    if (p.base_clean && p.meta.num_levels <= p.base_level + 1) {
+        T = p.tab;  // never dereferenced: no table look-up at a clean base level, no deeper level
+        __syncthreads();
+    } else {
+        T = load_tables(p.tab, p.n1, smem);  // ends with __syncthreads()
+    }
     int32_t* s_leaf = smem + 6 * p.n1;
     const int nb = 1 << (2 * p.base_level);
     const int32_t* src = p.node_leaf + off2d(p.base_level);
@@ -571,7 +584,8 @@ extern "C" int32_t g2pc_multisplit_rows(int64_t n, int32_t leaf_cap) {
 }
 
 extern "C" int g2pc_multisplit(const uint64_t* val_sorted, int64_t n, const void* proj, int32_t width, int32_t height,
-                               const int32_t* tables, int32_t num_levels, uint32_t level_mask, const int32_t* node_leaf,
+                               const int32_t* tables, int32_t num_levels, uint32_t level_mask, uint32_t clean_mask,
+                               const int32_t* node_leaf,
                                const g2pc_leaf_t* leaves, const int32_t* header, const uint32_t* fail, int32_t frame,
                                int32_t leaf_cap, uint32_t* matrix, uint32_t* inst_gid, void* stream) {
     G2PC_CHECK_ARG(n >= 0, "n < 0");
@@ -593,6 +607,7 @@ extern "C" int g2pc_multisplit(const uint64_t* val_sorted, int64_t n, const void
     p.node_leaf = node_leaf; p.header = header; p.fail = fail; p.frame = frame; p.leaves = leaves; p.matrix = matrix;
     p.inst_gid = inst_gid;
     p.leaf_cap = leaf_cap; p.grid_w = 0;
+    p.base_clean = (int32_t)((clean_mask >> p.base_level) & 1u);
     const int32_t chunks = (int32_t)((n + C - 1) / C);
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 256) return launch_multisplit<256>(p, chunks, st);
@@ -620,7 +635,7 @@ extern "C" int g2pc_multisplit_grid(const uint64_t* val_sorted, int64_t n, int32
     p.level_mask = 1u; p.base_level = 0;
     p.node_leaf = nullptr; p.header = header; p.fail = fail; p.frame = frame; p.leaves = leaves; p.matrix = matrix;
     p.inst_gid = inst_gid;
-    p.leaf_cap = leaf_cap; p.grid_w = grid_w;
+    p.leaf_cap = leaf_cap; p.grid_w = grid_w; p.base_clean = 1;
     const int32_t chunks = (int32_t)((n + C - 1) / C);
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 256) return launch_multisplit<256>(p, chunks, st);

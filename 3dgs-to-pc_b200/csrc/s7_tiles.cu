@@ -163,8 +163,7 @@ __global__ void __launch_bounds__(256) preprocess_tiles_kernel(const TilePrePara
             }
         }
         // Gaussians per tile; large rects are walked by the whole warp (all 32 lanes reach this point)
-        warp_for_each_node(ok ? rx0 : 1, ok ? rx1 - 1 : 0, ok ? ry0 : 1, ok ? ry1 - 1 : 0, 0u,
-                           [&](int tx_, int ty_, int, uint32_t) {
+        warp_for_each_node(range, 0u, [&](int tx_, int ty_, int, uint32_t) {
                                if (p.use_hist) atomicAdd(s_hist_t + ty_ * p.gx + tx_, 1u);
                                else atomicAdd(p.node_cnt + ty_ * p.gx + tx_, 1u);
                            });

@@ -35,16 +35,16 @@ SIGNATURES = {
                           _c_void_p, _c_void_p, ctypes.c_int, _i64, _c_void_p], ctypes.c_int),
     "g2pc_dump_eps": ([_c_void_p, _i64, _i32, _i32, _u64, _u32, _c_void_p, _c_void_p], ctypes.c_int),
     "g2pc_pack_geometry": ([_c_void_p, _c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p], ctypes.c_int),
-    "g2pc_preprocess": ([_c_void_p, _c_void_p, _c_void_p, _i32, _i32, _i64, _c_void_p, _c_void_p, _i32, _u32, _c_void_p,
-                         _c_void_p, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_preprocess": ([_c_void_p, _c_void_p, _c_void_p, _i32, _i32, _i64, _c_void_p, _c_void_p, _c_void_p, _i32, _u32,
+                         _u32, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
     "g2pc_depth_sort_workspace_bytes": ([_i64], ctypes.c_int64),
     "g2pc_depth_sort": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _i64, _c_void_p], ctypes.c_int),
     "g2pc_build_tree": ([_c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _i32, _i64, _i64,
                          _i64, _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
     "g2pc_multisplit_chunk": ([_i32], ctypes.c_int32),
     "g2pc_multisplit_rows": ([_i64, _i32], ctypes.c_int32),
-    "g2pc_multisplit": ([_c_void_p, _i64, _c_void_p, _i32, _i32, _c_void_p, _i32, _u32, _c_void_p, _c_void_p, _c_void_p,
-                         _c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_multisplit": ([_c_void_p, _i64, _c_void_p, _i32, _i32, _c_void_p, _i32, _u32, _u32, _c_void_p, _c_void_p,
+                         _c_void_p, _c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
     "g2pc_blend": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                     _c_void_p, _c_void_p, _i32, _i32, _f32, _f32, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
     "g2pc_accumulate": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p, _i32, _c_void_p], ctypes.c_int),

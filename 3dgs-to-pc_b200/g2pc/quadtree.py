@@ -83,6 +83,31 @@ class QuadtreeTables:
         return (cat(self.x, "start"), cat(self.x, "end"), cat(self.x, "flags"),
                 cat(self.y, "start"), cat(self.y, "end"), cat(self.y, "flags"))
 
+    def pixel_luts(self):
+        """Per level and axis, the node range of an interval as a lookup over PIXEL coordinates (uint16):
+            lo[q]  = first node i with end_i   > q   (q = floor(rect_min));  2^level if none
+            hi1[c] = 1 + last node i with start_i < c (c = ceil(rect_max));  0 if none
+        — exactly the strict float compares of gauss_render.py:308-310 (starts / ends are integers and non-decreasing).
+        Flat layout per level: [x lo (W)][x hi1 (W)][y lo (H)][y hi1 (H)], levels concatenated."""
+        out = []
+        for l in range(self.num_levels):
+            for ax, extent in ((self.x[l], self.width), (self.y[l], self.height)):
+                px = np.arange(extent)
+                lo = np.searchsorted(ax["end"], px, side="right")     # ends <= q are skipped
+                hi1 = np.searchsorted(ax["start"], px, side="left")    # starts < c
+                out += [lo.astype(np.uint16), hi1.astype(np.uint16)]
+        return np.concatenate(out)
+
+    def clean_level_mask(self):
+        """Bit l set iff no node of level l is dropped or degenerate (end < start) on either axis."""
+        mask = 0
+        for l in range(self.num_levels):
+            ok = all(((ax[l]["flags"] & FLAG_DROPPED) == 0).all() and (ax[l]["end"] > ax[l]["start"]).all()
+                     for ax in (self.x, self.y))
+            if ok:
+                mask |= 1 << l
+        return mask
+
     def candidate_level_mask(self):
         """Bit l set iff level l has a live node that is not forced to split by its size (a leaf candidate)."""
         mask = 0

@@ -147,7 +147,12 @@ class GaussPythonRenderer(FrameQueue):
             base = (mask & -mask).bit_length() - 1
             if base > 8:
                 raise capi.G2pcError("image too large for the packed node range (first leaf level deeper than 8)")
+            luts = qt.pixel_luts()
+            if luts.shape[0] % 2:
+                luts = np.concatenate([luts, np.zeros(1, np.uint16)])
             t = dict(qt=qt, tables=torch.from_numpy(flat).to(dev), level_mask=mask, base_level=base,
+                     clean_mask=qt.clean_level_mask(),
+                     luts=torch.from_numpy(luts.view(np.int16).copy()).to(dev),
                      slots=[dict(node_cnt=torch.zeros((qt.nodes_2d,), dtype=torch.int32, device=dev),
                                  node_state=torch.zeros((qt.nodes_2d,), dtype=torch.uint8, device=dev),
                                  node_leaf=torch.full((qt.nodes_2d,), -1, dtype=torch.int32, device=dev),
@@ -218,7 +223,8 @@ class GaussPythonRenderer(FrameQueue):
         self._buffers(t, sl)
         capi.call("g2pc_preprocess", capi.ptr(self._geom), capi.ptr(self._colour_f32) if self.shs is None else None,
                   capi.ptr(self.shs), int(self.shs.shape[-1]) if self.shs is not None else 0, self.sh_degree, n,
-                  ctypes.byref(cam), capi.ptr(t["tables"]), qt.num_levels, t["level_mask"], capi.ptr(sl["proj"]),
+                  ctypes.byref(cam), capi.ptr(t["tables"]), capi.ptr(t["luts"]), qt.num_levels, t["level_mask"],
+                  t["clean_mask"], capi.ptr(sl["proj"]),
                   capi.ptr(ts["node_cnt"]), capi.ptr(sl["depth_key"]), capi.ptr(sl["val"]), st)
         capi.call("g2pc_depth_sort", capi.ptr(sl["depth_key"]), capi.ptr(sl["val"]), n, capi.ptr(sl["val_sorted"]),
                   capi.ptr(sl["depth_ws"]), sl["depth_ws"].numel(), st)
@@ -227,7 +233,8 @@ class GaussPythonRenderer(FrameQueue):
                   capi.ptr(ts["leaf_order"]), t["leaf_cap"], self._inst_cap, t["pix_cap"], sl["matrix"].numel(),
                   t["chunks"], frame, capi.ptr(sl["hdr"]), capi.ptr(self._fail), capi.ptr(sl["work"]), st)
         capi.call("g2pc_multisplit", capi.ptr(sl["val_sorted"]), n, capi.ptr(sl["proj"]), W, H, capi.ptr(t["tables"]),
-                  qt.num_levels, t["level_mask"], capi.ptr(ts["node_leaf"]), capi.ptr(ts["leaves"]), capi.ptr(sl["hdr"]),
+                  qt.num_levels, t["level_mask"], t["clean_mask"], capi.ptr(ts["node_leaf"]), capi.ptr(ts["leaves"]),
+                  capi.ptr(sl["hdr"]),
                   capi.ptr(self._fail), frame, t["leaf_cap"], capi.ptr(sl["matrix"]), capi.ptr(sl["inst_gid"]), st)
         self._last_tables, self._last_slot = t, slot
         return sl["hdr"]

@@ -177,7 +177,8 @@ typedef struct {
 /* Quadtree tables (host-built, g2pc/quadtree.py): `tables` = 6 int32 arrays of n1 = 2^num_levels - 1 entries each,
  * concatenated: x start, x end (inclusive), x flags, y start, y end, y flags; level l at offset 2^l - 1.
  * 2-D node index = (4^l - 1)/3 + iy * 2^l + ix.  level_mask: bit l set iff level l has nodes small enough to be
- * leaves (a node larger than max_tile_size splits whatever it holds; its count is never collected). */
+ * leaves.  clean_mask: bit l set iff level l has no dropped / degenerate node on either axis (then the membership of
+ * an interval is exactly its looked-up node range and the kernels skip the per-node table checks). */
 
 /* Once per renderer: geom (n x 48 bytes, 16-byte aligned) = {x,y,z,S00} {S01,S02,S11,S12} {S22,log2(opacity),0,0}
  * from xyz (n,3), cov (n,3,3), opacity (n) — the coalesced 16-byte-load form the per-camera kernel reads. */
@@ -190,11 +191,13 @@ int g2pc_pack_geometry(const float* xyz, const float* cov, const float* opacity,
  * proj: n x 48 bytes (3 float4: {mx,my,c00',c01'} {c11',log2(opacity),r,g} {b,depth,radius,valid}).
  * node_cnt: one uint32 per 2-D node, zero on entry (g2pc_build_tree clears it again).  depth_key (n) uint32:
  * bits(-z_view), 0xFFFFFFFF if behind the camera.  val (n) uint64: (node range at the first candidate level, 8 bits per
- * bound: xlo | xhi<<8 | ylo<<16 | yhi<<24) << 32 | Gaussian index. */
+ * bound: xlo | xhi<<8 | ylo<<16 | yhi<<24) << 32 | Gaussian index.
+ * luts (uint16, 4-byte aligned): per level [x lo (W)][x hi+1 (W)][y lo (H)][y hi+1 (H)] — node range of an interval as
+ * a lookup over pixel coordinates, lo[floor(min)] .. hi1[ceil(max)] - 1 (g2pc/quadtree.py QuadtreeTables.pixel_luts). */
 int g2pc_preprocess(const void* geom, const float* colours, const float* shs, int32_t sh_stride, int32_t sh_degree,
-                    int64_t n, const g2pc_camera_t* cam_host, const int32_t* tables, int32_t num_levels,
-                    uint32_t level_mask, void* proj, uint32_t* node_cnt, uint32_t* depth_key, uint64_t* val,
-                    void* stream);
+                    int64_t n, const g2pc_camera_t* cam_host, const int32_t* tables, const uint16_t* luts,
+                    int32_t num_levels, uint32_t level_mask, uint32_t clean_mask, void* proj, uint32_t* node_cnt,
+                    uint32_t* depth_key, uint64_t* val, void* stream);
 
 /* S4a.  val_sorted[k] = val of the k-th nearest Gaussian (stable radix sort of depth_key: ties keep index order, the
  * reference's torch.sort is unstable there, gauss_render.py:340-344).  cub::DeviceRadixSort (library call). */
@@ -220,8 +223,9 @@ int g2pc_build_tree(const int32_t* tables, int32_t num_levels, int32_t max_gauss
 int32_t g2pc_multisplit_chunk(int32_t leaf_cap);
 int32_t g2pc_multisplit_rows(int64_t n, int32_t leaf_cap); /* rows of `matrix` needed (chunks + one per persistent CTA) */
 int g2pc_multisplit(const uint64_t* val_sorted, int64_t n, const void* proj, int32_t width, int32_t height,
-                    const int32_t* tables, int32_t num_levels, uint32_t level_mask, const int32_t* node_leaf,
-                    const g2pc_leaf_t* leaves, const int32_t* header, const uint32_t* fail, int32_t frame,
+                    const int32_t* tables, int32_t num_levels, uint32_t level_mask, uint32_t clean_mask,
+                    const int32_t* node_leaf, const g2pc_leaf_t* leaves, const int32_t* header, const uint32_t* fail,
+                    int32_t frame,
                     int32_t leaf_cap, uint32_t* matrix, uint32_t* inst_gid, void* stream);
 
 /* S5.  Front-to-back blend of every leaf (gauss_render.py:337-369) + per-Gaussian maximum contribution / arg-max pixel

@@ -8,7 +8,9 @@ mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv \
     python profiles/recipes/colour_step.py --workload $WL --cams 3 > gpurun_out/${TAG}_launches.log 2>&1
 ncu --set full --clock-control none --import-source on \
-    -k regex:'preprocess_kernel|tree_kernel|ms_count|ms_scan|ms_scatter|blend_kernel|accumulate_kernel' -s 7 -c 7 \
+    -k regex:'preprocess_kernel|tree_kernel|ms_count|ms_scan|ms_scatter|blend_kernel|accumulate_kernel' -s 9 -c 9 \
     -o gpurun_out/${TAG}_colour -f python profiles/recipes/colour_step.py --workload $WL --cams 2 > gpurun_out/${TAG}_colour.log 2>&1
 ncu -i gpurun_out/${TAG}_colour.ncu-rep --page raw --csv > gpurun_out/${TAG}_colour_raw.csv 2>/dev/null
-ncu -i gpurun_out/${TAG}_colour.ncu-rep --page source --csv -k regex:blend_kernel > gpurun_out/${TAG}_blend_src.csv 2>/dev/null
+for K in blend_kernel preprocess_kernel ms_scatter ms_count; do
+  ncu -i gpurun_out/${TAG}_colour.ncu-rep --page source --csv -k regex:$K > gpurun_out/${TAG}_${K}_src.csv 2>/dev/null
+done
