@@ -125,7 +125,53 @@ def local_bin_counts(bins, local_hist):
     return out
 
 
-def convert_gaussians_to_pc_sharded(scene, transforms, intrinsics, settings, render_shs=False, gather=False):
+LAST_PHASES = {}
+
+
+class _Phases:
+    """Per-rank wall-clock phases of one sharded step (device-synchronised at every boundary, so only used in a separate
+    profiling step: G2PC_PHASE_TIMING=1 or bench.py's timeline step).  There is no nsys in this image; this is the
+    per-rank timeline that names what is left outside the kernels."""
+
+    def __init__(self, enabled, device):
+        import time
+        self.enabled, self.device, self.t, self.out, self.time = enabled, device, None, {}, time
+        if enabled:
+            torch.cuda.synchronize(device)
+            self.t = time.perf_counter()
+
+    def mark(self, name):
+        if not self.enabled:
+            return
+        torch.cuda.synchronize(self.device)
+        now = self.time.perf_counter()
+        self.out[name] = self.out.get(name, 0.0) + (now - self.t) * 1e3
+        self.t = now
+
+
+def upload_sharded(host_scene, device):
+    """e2e path of an N-rank run: every rank copies only ITS row range of each (pinned) host array over PCIe and the ranks
+    exchange the shards with one in-place all_gather per array over NVLink — instead of N full host->device uploads
+    (1.44 GB each at C3).  Returns the full device tensors on every rank."""
+    rank, W = world()
+    out = {}
+    for k, v in host_scene.items():
+        n = v.shape[0]
+        if W == 1:
+            out[k] = v.to(device, non_blocking=True)
+            continue
+        per = (n + W - 1) // W
+        full = torch.empty((per * W,) + tuple(v.shape[1:]), dtype=v.dtype, device=device)
+        b, e = min(n, rank * per), min(n, (rank + 1) * per)
+        if e > b:
+            full[b:e].copy_(v[b:e], non_blocking=True)
+        dist.all_gather_into_tensor(full, full[rank * per:(rank + 1) * per])  # in place: shard r sits at r * per
+        out[k] = full[:n]
+    return out
+
+
+def convert_gaussians_to_pc_sharded(scene, transforms, intrinsics, settings, render_shs=False, gather=False,
+                                    phase_timing=None):
     """The device-resident pipeline of gauss_to_pc.convert_gaussians_to_pc on W ranks.
 
     scene: dict of device tensors (xyz, scales, rots, colours, opacities, shs) holding the WHOLE scene on every rank.
@@ -141,14 +187,19 @@ def convert_gaussians_to_pc_sharded(scene, transforms, intrinsics, settings, ren
     if s.cull_large_percentage > 0.0 or s.generate_mesh:
         raise NotImplementedError("the sharded pipeline covers the visibility / opacity / bounding-box / surface-distance "
                                   "culls; size-percentile culls and meshing run through convert_gaussians_to_pc")
+    import os
+    global LAST_PHASES
+    ph = _Phases(bool(int(os.environ.get("G2PC_PHASE_TIMING", "0"))) if phase_timing is None else phase_timing,
+                 scene["xyz"].device)
     n_all = scene["xyz"].shape[0]
     gaussians = Gaussians(scene["xyz"], scene["scales"], scene["rots"], scene["colours"], scene["opacities"],
                           shs=scene.get("shs"))
     if s.calculate_normals:
         gaussians.calculate_normals()
+    ph.mark("covariances+normals")
 
     contributions = None
-    keep = torch.ones(n_all, dtype=torch.bool, device=scene["xyz"].device)
+    max_contrib, surface_mask = None, None
     if s.render_colours:
         renderer = get_renderer(s.renderer_type, gaussians.xyz, torch.unsqueeze(torch.clone(gaussians.opacities), 1),
                                 gaussians.colours, gaussians.covariances, shs=gaussians.shs if render_shs else None,
@@ -168,6 +219,7 @@ def convert_gaussians_to_pc_sharded(scene, transforms, intrinsics, settings, ren
                              sh_degree=s.max_sh_degree, white_bkgd=True, mask=None)
             renderer(cam, camera_index=ci)
         renderer.flush()
+        ph.mark("colour stage (this rank's cameras)")
         merge_colour_accumulators(renderer.gaussian_max_contribution, renderer.gaussian_colours, first_cam)
         if s.renderer_type == "cuda" and W > 1:
             # CUDA back-end extras (gaussian_pointcloud_rasterization/__init__.py:152-158): the total contribution is a
@@ -178,31 +230,27 @@ def convert_gaussians_to_pc_sharded(scene, transforms, intrinsics, settings, ren
                 dist.all_reduce(renderer.gaussian_min_surface_distance, op=dist.ReduceOp.MIN)
         gaussians.colours = renderer.get_gaussian_colours()
         if s.surface_distance_std is not None:
-            keep &= renderer.get_gaussians_with_low_surface_distance()
+            surface_mask = renderer.get_gaussians_with_low_surface_distance()
         if s.remove_unrendered_gaussians:
-            keep &= renderer.get_visible_gaussians()
-        if s.min_opacity > 0.0:
-            keep &= gaussians.opacities > s.min_opacity
-        for bound, cmp in ((s.bounding_box_min, torch.gt), (s.bounding_box_max, torch.lt)):
-            if bound is not None:
-                keep &= cmp(gaussians.xyz, torch.as_tensor(bound, dtype=gaussians.xyz.dtype, device=keep.device)).all(dim=1)
+            max_contrib = renderer.gaussian_max_contribution
         if s.prioritise_visible_gaussians:
             contributions = renderer.get_total_gaussian_contributions()
         g2p.LAST_RENDER_STATS = {"stats": renderer._stats, "replays": renderer.replays}
+        vis_thr = renderer.visible_gaussian_threshold
         del renderer
+        ph.mark("accumulator merge (NCCL)")
     else:
         gaussians.colours = gaussians.colours * 255
+        vis_thr = 0.0
 
-    # ---- sampling: this rank owns the Gaussians [b, e) -----------------------------------------------------------
+    # ---- sampling: this rank owns the Gaussians [b, e): every cull + the index shard in ONE fused mask / compaction ------
     b, e = gaussian_shard(n_all)
-    local = torch.zeros_like(keep)
-    local[b:e] = True
-    sel = keep & local
-    gid = torch.nonzero(sel).squeeze(1)
-    gaussians.add_gaussians_to_cull(sel)
-    gaussians.filter_gaussians()
+    gid = gaussians.fused_cull(max_contribution=max_contrib, visibility_threshold=vis_thr, min_opacity=s.min_opacity,
+                               bounding_box_min=s.bounding_box_min, bounding_box_max=s.bounding_box_max,
+                               extra_mask=surface_mask, index_range=(b, e))
     if contributions is not None:
-        contributions = contributions[sel]
+        contributions = contributions[gid]
+    ph.mark("cull + compaction")
     valid = gaussians.validate_covariances()
     gid = gid[valid]
     if contributions is not None:
@@ -218,4 +266,6 @@ def convert_gaussians_to_pc_sharded(scene, transforms, intrinsics, settings, ren
         s.mahalanobis_distance_std, s.exact_num_points, attempts, config.SEED, 0, gids=gid, global_bins=bins)
     t = int(total.item())
     g2p._check_status(status)
+    ph.mark("validate + point budget + sampling")
+    LAST_PHASES = ph.out
     return g2p.PointCloudData(points=pts[:t], colours=cols[:t], normals=(nrm[:t] if nrm is not None else None))

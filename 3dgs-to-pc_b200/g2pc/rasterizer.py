@@ -148,7 +148,7 @@ class GaussianRasterizer(FrameQueue):
             self._cam_dist = torch.empty((m,), dtype=torch.int32, device=dev)
             capi.call("g2pc_fill_u32", capi.ptr(self._cam_dist), FLT_MAX_BITS, m, capi.stream_ptr(dev))
         self._stats = torch.zeros((capi.STAT_WORDS,), dtype=torch.int64, device=dev)
-        self._inst_cap = max(8 * n, 1 << 16)
+        self._inst_cap = max(12 * n, 1 << 16)  # 16x16 tiles: a splat of radius ~15 px touches 9-16 of them
         self._res = {}
         self._last_slot = 0
         self.last_stats = {}

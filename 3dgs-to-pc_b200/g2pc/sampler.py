@@ -99,39 +99,52 @@ class SamplePlan:
             raise capi.G2pcError("attempts_stored must be <= 255 (8-bit attempt tag of the emit pass)")
         if any(k >= (1 << 24) for (k, _) in bin_k_count):
             raise capi.G2pcError("more than 2^24 - 1 samples per Gaussian per attempt (24-bit sample tag of the emit pass)")
-        tiles, units, unit_src = [], [], []
-        j0 = 0
-        tile_base_index = 0
-        centre_lens = []
+        # vectorised over bins (exact_num_points makes one bin per distinct count: thousands of bins x attempts)
         A = attempts_stored
-        for (k, count) in bin_k_count:
-            lpg = _lpg_for(k)
-            per_tile = 256 // lpg
-            nt = (count + per_tile - 1) // per_tile
-            starts = j0 + np.arange(nt, dtype=np.int64) * per_tile
-            counts = np.minimum(per_tile, j0 + count - starts)
-            t = np.stack([starts, counts, np.full(nt, k), np.full(nt, lpg)], axis=1)
-            tiles.append(t)
-            if include_centres:
-                units.append(np.array([[-1, j0, count, 0]], dtype=np.int64))
-                unit_src.append(np.array([-(len(centre_lens) + 1)], dtype=np.int64))
-                centre_lens.append(count)
-            if k > 0:
-                tidx = tile_base_index + np.arange(nt, dtype=np.int64)
-                for a in range(A):
-                    u = np.stack([np.full(nt, a), starts, counts, np.full(nt, k)], axis=1)
-                    units.append(u)
-                    unit_src.append(tidx * A + a)
-            tile_base_index += nt
-            j0 += count
+        ks = np.asarray([k for (k, _) in bin_k_count], dtype=np.int64)
+        counts = np.asarray([c for (_, c) in bin_k_count], dtype=np.int64)
+        nb = ks.shape[0]
+        lpgs = np.asarray([_lpg_for(int(k)) for k in ks], dtype=np.int64) if nb else np.zeros(0, np.int64)
+        per_tile = 256 // np.maximum(lpgs, 1)
+        nts = (counts + per_tile - 1) // np.maximum(per_tile, 1)
+        j0s = np.concatenate([[0], np.cumsum(counts)])[:-1] if nb else np.zeros(0, np.int64)
+        tile_base = np.concatenate([[0], np.cumsum(nts)])[:-1] if nb else np.zeros(0, np.int64)
+        nt_total = int(nts.sum()) if nb else 0
+        # tiles: bin of every tile, position inside the bin
+        tbin = np.repeat(np.arange(nb), nts)
+        tpos = np.arange(nt_total) - np.repeat(tile_base, nts)
+        tstart = j0s[tbin] + tpos * per_tile[tbin]
+        tcount = np.minimum(per_tile[tbin], j0s[tbin] + counts[tbin] - tstart)
+        tiles_arr = np.stack([tstart, tcount, ks[tbin], lpgs[tbin]], axis=1) if nt_total else np.zeros((0, 4), np.int64)
+        # units in output order: per bin [centre unit][attempt 0: tiles..][attempt 1: tiles..]...
+        has_k = ks > 0
+        per_bin_units = (1 if include_centres else 0) + np.where(has_k, A * nts, 0)
+        ubase = np.concatenate([[0], np.cumsum(per_bin_units)])[:-1] if nb else np.zeros(0, np.int64)
+        nu_total = int(per_bin_units.sum()) if nb else 0
+        units_arr = np.zeros((nu_total, 4), dtype=np.int64)
+        src_arr = np.zeros((nu_total,), dtype=np.int64)
+        if include_centres and nb:
+            units_arr[ubase] = np.stack([np.full(nb, -1), j0s, counts, np.zeros(nb, np.int64)], axis=1)
+            src_arr[ubase] = nt_total * A + np.arange(nb)  # lengths gathered from concat([tile_totals, centre_lens])
+        if nt_total:
+            tk = has_k[tbin]
+            t_idx = np.nonzero(tk)[0]            # tiles of bins with samples
+            tb = tbin[t_idx]
+            a = np.arange(A)
+            # unit index of (tile t, attempt a) = ubase[bin] + centre + a * nts[bin] + tpos
+            uidx = (ubase[tb] + (1 if include_centres else 0) + tpos[t_idx])[:, None] + a[None, :] * nts[tb][:, None]
+            units_arr[uidx.reshape(-1)] = np.stack([np.broadcast_to(a[None, :], uidx.shape).reshape(-1),
+                                                    np.repeat(tstart[t_idx], A), np.repeat(tcount[t_idx], A),
+                                                    np.repeat(ks[tb], A)], axis=1)
+            src_arr[uidx.reshape(-1)] = (t_idx[:, None] * A + a[None, :]).reshape(-1)
+        j0 = int(counts.sum()) if nb else 0
+        centre_lens = counts.tolist() if include_centres else []
         self.n = j0
         self.attempts_stored = A
-        self.tiles = (np.concatenate(tiles, 0) if tiles else np.zeros((0, 4))).astype(np.int32)
-        self.units = (np.concatenate(units, 0) if units else np.zeros((0, 4))).astype(np.int32)
-        src = np.concatenate(unit_src, 0) if unit_src else np.zeros((0,), dtype=np.int64)
-        # lengths are gathered from concat([tile_totals (num_tiles*A), centre_lens]); negative src -> centre slot
-        nt_total = self.tiles.shape[0]
-        self.unit_src = np.where(src >= 0, src, nt_total * A + (-src - 1)).astype(np.int64)
+        self.tiles = tiles_arr.astype(np.int32)
+        self.units = units_arr.astype(np.int32)
+        # lengths are gathered from concat([tile_totals (num_tiles*A), centre_lens])
+        self.unit_src = src_arr.astype(np.int64)
         self.centre_lens = np.asarray(centre_lens, dtype=np.int64)
         self.capacity = int(sum(c * (k + (1 if include_centres else 0)) for (k, c) in bin_k_count))
 

@@ -81,10 +81,16 @@ def eigvals_sym3(covariances):
 class Gaussians():
     """
     Manages all loaded gaussians in the renderer  (reference: gauss_handler.py:65-279)
+
+    `scales`, `rots` and `shs` are not read by anything after the colour stage; filters applied through fused_cull() keep
+    them lazily (original tensor + pending row index) and materialise them on first access, so the 576 MB SH gather of a
+    3 M-Gaussian scene is only paid by a caller that actually looks at them.
     """
+    _LAZY = ("scales", "rots", "shs")
 
     def __init__(self, xyz, scales, rots, colours, opacities, shs=None):
         capi.require_cuda(xyz, scales, rots, colours, opacities, shs)
+        self._lazy = {}
         self.xyz = xyz
         self.scales = scales
         self.rots = rots
@@ -103,8 +109,91 @@ class Gaussians():
 
         self.set_default_filter()
 
+    # ---- lazily filtered attributes ---------------------------------------------------------------------------------
+    def __setattr__(self, name, value):
+        if name in Gaussians._LAZY:
+            self.__dict__["_lazy"][name] = (value, None)
+        else:
+            object.__setattr__(self, name, value)
+
+    def __getattr__(self, name):  # only reached for names without a regular attribute
+        if name in Gaussians._LAZY:
+            tensor, idx = self.__dict__["_lazy"][name]
+            if idx is not None and tensor is not None:
+                tensor = tensor.index_select(0, idx)
+                self.__dict__["_lazy"][name] = (tensor, None)
+            return tensor
+        raise AttributeError(name)
+
+    def _lazy_filter(self, index64):
+        for name, (tensor, idx) in list(self._lazy.items()):
+            if tensor is not None:
+                self._lazy[name] = (tensor, index64 if idx is None else idx.index_select(0, index64))
+
+    def fused_cull(self, max_contribution=None, visibility_threshold=0.0, min_opacity=0.0, bounding_box_min=None,
+                   bounding_box_max=None, surface_distance=None, surface_threshold=None, extra_mask=None,
+                   index_range=None):
+        """All culls of gauss_to_pc.py:483-496 + filter_gaussians (gauss_handler.py:171-193) as ONE mask / compaction:
+        g2pc_cull_select builds the ascending list of kept rows, g2pc_gather_rows compacts xyz, colours, opacities,
+        covariances, normals and ids in one call; scales / rots / shs follow lazily.  Also honours the pending
+        filter_indices.  Returns the int64 row index of the kept Gaussians (use it like the reference's boolean mask)."""
+        import ctypes
+        n = self.xyz.shape[0]
+        dev = self.xyz.device
+        st = capi.stream_ptr(dev)
+        f32 = lambda t: None if t is None else t.to(torch.float32).contiguous()
+        mc, op, xyz, sd = f32(max_contribution), f32(self.opacities) if min_opacity > 0.0 else None, f32(self.xyz), f32(surface_distance)
+        extra = self.filter_indices if not bool(getattr(self, "_filter_is_default", False)) else None
+        if extra_mask is not None:
+            extra = extra_mask if extra is None else (extra & extra_mask)
+        extra_u8 = None if extra is None else extra.to(torch.uint8).contiguous()
+        thr = None
+        if sd is not None:
+            thr = torch.as_tensor(surface_threshold, dtype=torch.float32, device=dev).reshape(1).contiguous()
+        bmin = (ctypes.c_float * 3)(*[float(v) for v in bounding_box_min]) if bounding_box_min is not None else None
+        bmax = (ctypes.c_float * 3)(*[float(v) for v in bounding_box_max]) if bounding_box_max is not None else None
+        lo, hi = (0, n) if index_range is None else index_range
+        index = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+        count = torch.zeros((1,), dtype=torch.int64, device=dev)
+        ws = torch.empty((max(int(capi.load().g2pc_cull_workspace_bytes(n)), 8),), dtype=torch.uint8, device=dev)
+        capi.call("g2pc_cull_select", capi.ptr(mc), float(visibility_threshold), capi.ptr(op), float(min_opacity),
+                  capi.ptr(xyz), bmin, bmax, capi.ptr(sd), capi.ptr(thr), capi.ptr(extra_u8), int(lo), int(hi), n,
+                  capi.ptr(index), capi.ptr(count), capi.ptr(ws), ws.numel(), st)
+        m = int(count.item())  # the one host read: output sizes
+        index = index[:m]
+        names = [k for k in ("xyz", "colours", "opacities", "covariances", "normals", "ids") if getattr(self, k) is not None]
+        srcs = [getattr(self, k).contiguous() for k in names]
+        dsts = [torch.empty((m,) + tuple(s.shape[1:]), dtype=s.dtype, device=dev) for s in srcs]
+        if m > 0:
+            k = len(srcs)
+            sp = (ctypes.c_void_p * k)(*[s.data_ptr() for s in srcs])
+            dp = (ctypes.c_void_p * k)(*[d.data_ptr() for d in dsts])
+            rb = (ctypes.c_int32 * k)(*[int(s[0].numel() * s.element_size()) if s.dim() > 1 else int(s.element_size()) for s in srcs])
+            capi.call("g2pc_gather_rows", capi.ptr(index), m, k, sp, dp, rb, st)
+        for name, d in zip(names, dsts):
+            setattr(self, name, d)
+        index64 = index.to(torch.int64)
+        self._lazy_filter(index64)
+        self.set_default_filter()
+        return index64
+
+    def points_per_gaussian(self, num_points, contributions=None):
+        """get_gaussian_magnitudes (gauss_handler.py:252-279) + distribute_points (gauss_to_pc.py:73-90) as one
+        entry point without a host round trip.  Returns (points_per_gaussian int32, magnitudes float64)."""
+        n = self.xyz.shape[0]
+        dev = self.xyz.device
+        contrib = (self.opacities if contributions is None else contributions).to(torch.float32).reshape(-1).contiguous()
+        cov = self.covariances.to(torch.float32).contiguous()
+        mag = torch.empty((max(n, 1),), dtype=torch.float64, device=dev)
+        ppg = torch.zeros((max(n, 1),), dtype=torch.int32, device=dev)
+        ws = torch.empty((max(int(capi.load().g2pc_ppg_workspace_bytes(n)) // 8 + 1, 1),), dtype=torch.float64, device=dev)
+        capi.call("g2pc_points_per_gaussian", capi.ptr(cov), capi.ptr(contrib), n, float(num_points), capi.ptr(mag),
+                  capi.ptr(ppg), capi.ptr(ws), ws.numel() * 8, capi.stream_ptr(dev))
+        return ppg[:n], mag[:n]
+
     def set_default_filter(self):
         self.filter_indices = torch.ones((self.xyz.shape[0],), dtype=torch.bool, device=self.xyz.device)
+        self._filter_is_default = True
 
     def calculate_normals(self):
         """Normal of each Gaussian = rotated axis of its smallest scale (gauss_handler.py:89-106)."""
@@ -165,6 +254,7 @@ class Gaussians():
 
     def add_gaussians_to_cull(self, indices_to_cull):
         self.filter_indices = self.filter_indices & indices_to_cull
+        self._filter_is_default = False
 
     def filter_gaussians(self):
         """Keep the Gaussians selected by filter_indices (gauss_handler.py:171-193); returns the mask used."""
@@ -193,6 +283,7 @@ class Gaussians():
         """Drop Gaussians with opacity <= min_opacity (gauss_handler.py:195-203)."""
         if min_opacity > 0.0:
             self.filter_indices = self.filter_indices & (self.opacities > min_opacity)
+            self._filter_is_default = False
 
     def apply_bounding_box(self, bounding_box_min, bounding_box_max):
         """Drop Gaussians outside the open box (gauss_handler.py:205-224)."""
@@ -204,6 +295,7 @@ class Gaussians():
             hi = torch.as_tensor(bounding_box_max, dtype=self.xyz.dtype, device=self.xyz.device)
             valid &= (self.xyz < hi).all(dim=1)
         self.filter_indices = self.filter_indices & valid
+        self._filter_is_default = False
 
     def cull_large_gaussians(self, cull_gauss_size_percent):
         """Remove the largest `cull_gauss_size_percent` fraction of Gaussians by magnitude.
@@ -218,6 +310,7 @@ class Gaussians():
             keep = torch.zeros(sizes.shape[0], dtype=torch.bool, device=sizes.device)
             keep[order[:cull_index]] = True
             self.filter_indices = self.filter_indices & keep
+            self._filter_is_default = False
 
     def get_gaussian_magnitudes(self, contributions=None):
         """sqrt(ellipsoid surface area) * contribution, f64 (gauss_handler.py:252-279)."""

@@ -168,13 +168,13 @@ def generate_pointcloud(gaussians, num_points, contributions=None, mahalanobis_d
     seed = config.SEED if seed is None else seed
     call_id = sampler.next_call_id() if call_id is None else call_id
 
-    gaussian_sizes = gaussians.get_gaussian_magnitudes(contributions=contributions)
+    # magnitudes (gauss_handler.py:252-279) and the point budget (distribute_points, :73-90) on the device, no host sync
+    points_per_gaussian, _ = gaussians.points_per_gaussian(num_points, contributions)
 
     if not quiet:
         print("Distributed Points to Gaussians")
         print()
 
-    points_per_gaussian = distribute_points(gaussian_sizes, num_points).type(torch.int)
     res = sample_points_per_gaussian(gaussians.xyz, gaussians.covariances, gaussians.colours,
                                      gaussians.normals if calculate_normals else None, points_per_gaussian,
                                      mahalanobis_distance_std, exact_num_points, num_sample_attempts, seed, call_id,
@@ -309,17 +309,17 @@ def convert_gaussians_to_pc(xyz, scales, rots, colours, opacities, shs, transfor
 
         gaussians.colours = gaussian_renderer.get_gaussian_colours()
 
+        # every cull of gauss_to_pc.py:483-496 in one fused mask + compaction (csrc/s8_cull.cu): surface distance,
+        # visibility, min opacity, bounding box (+ the size-percentile cull, which needs a sort, through filter_indices)
+        surface_mask = None
         if s.surface_distance_std is not None:
-            gaussians.add_gaussians_to_cull(gaussian_renderer.get_gaussians_with_low_surface_distance())
-
-        if s.remove_unrendered_gaussians:
-            gaussians.add_gaussians_to_cull(gaussian_renderer.get_visible_gaussians())
-
-        gaussians.apply_min_opacity(s.min_opacity)
-        gaussians.apply_bounding_box(s.bounding_box_min, s.bounding_box_max)
+            surface_mask = gaussian_renderer.get_gaussians_with_low_surface_distance()
         gaussians.cull_large_gaussians(s.cull_large_percentage)
-
-        culled_indices = gaussians.filter_gaussians()
+        gaussian_renderer.flush() if hasattr(gaussian_renderer, "flush") else None
+        culled_indices = gaussians.fused_cull(
+            max_contribution=gaussian_renderer.gaussian_max_contribution if s.remove_unrendered_gaussians else None,
+            visibility_threshold=gaussian_renderer.visible_gaussian_threshold, min_opacity=s.min_opacity,
+            bounding_box_min=s.bounding_box_min, bounding_box_max=s.bounding_box_max, extra_mask=surface_mask)
 
         say(f"\nNumber Gaussians after Culling: {gaussians.xyz.shape[0]}")
 

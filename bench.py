@@ -173,10 +173,13 @@ def run_ours(args):
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values()) + len(cams) * 64
 
     def upload():
+        if world > 1:  # every rank uploads its row range, the shards are exchanged over NVLink (g2pc/dist.py)
+            return gdist.upload_sharded(host, dev)
         return {k: v.to(dev, non_blocking=True) for k, v in host.items()}
 
     if world > 1:
         from g2pc import dist as gdist
+        h2d_bytes = (h2d_bytes + world - 1) // world  # per rank, per step
         runner = lambda d: gdist.convert_gaussians_to_pc_sharded(d, transforms, intrinsics, st, render_shs=wl["sh"] > 0)
     else:
         def runner(d):
@@ -259,6 +262,15 @@ def run_ours(args):
     warp_gaussians = int(rs[0].item()) if rs is not None else 0  # the renderer of the profiled step only
     kernel_ms = {k.replace("g2pc_", ""): round(float(np.sum(v)), 3) for k, v in timing.items() if v}
     roof, roofs = rooflines(wl, timing, warp_gaussians, g2p, pc, world, clk.summary())
+    rank_phases = None
+    if world > 1:
+        # per-rank timeline of one extra step (device-synchronised at every phase boundary: not a timed step)
+        sampler.reset_call_counter(0)
+        gdist.convert_gaussians_to_pc_sharded(resident, transforms, intrinsics, st, render_shs=wl["sh"] > 0,
+                                              phase_timing=True)
+        mine = {k: round(v, 2) for k, v in gdist.LAST_PHASES.items()}
+        rank_phases = [None] * world
+        dist.all_gather_object(rank_phases, mine)
 
     if rank != 0:
         if world > 1:
@@ -293,6 +305,8 @@ def run_ours(args):
         "kernel_ms_per_step": kernel_ms,
         "frame_replays": getattr(g2p, "LAST_RENDER_STATS", {}).get("replays", 0),
     }
+    if rank_phases is not None:
+        line["rank_phases_ms"] = rank_phases
     line.update(extras)
     print(json.dumps(line))
     if world > 1:

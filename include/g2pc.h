@@ -128,6 +128,32 @@ int g2pc_sample_emit(const void* records, const uint32_t* xl, int64_t n, const g
 int g2pc_dump_eps(const int64_t* gids, int64_t n_gids, int32_t k, int32_t attempt, uint64_t seed,
                   uint32_t call_id, float* eps, void* stream);
 
+/* ---- N4 / N1: culls and point budget (s8_cull.cu) ----------------------------------------------------------------- */
+/* Fused cull + compaction.  Replaces the mask chain of gauss_to_pc.py:483-496 and Gaussians.filter_gaussians
+ * (gauss_handler.py:171-193: one boolean-index pass and one host sync per array).  keep(i) = lo <= i < hi
+ * && max_contrib[i] > vis_threshold && opacity[i] > min_opacity && bbox_min < xyz[i] < bbox_max (open box)
+ * && surface_dist[i] < *surface_threshold_dev && extra_mask[i]; every criterion whose array is NULL is skipped
+ * (bbox_*_host: 3 host floats or NULL).  index: ascending row numbers of the kept Gaussians (capacity n int32);
+ * count: one int64 in device memory.  workspace: g2pc_cull_workspace_bytes(n). */
+int64_t g2pc_cull_workspace_bytes(int64_t n);
+int g2pc_cull_select(const float* max_contrib, float vis_threshold, const float* opacity, float min_opacity,
+                     const float* xyz, const float* bbox_min3_host, const float* bbox_max3_host,
+                     const float* surface_dist, const float* surface_threshold_dev, const uint8_t* extra_mask,
+                     int64_t lo, int64_t hi, int64_t n, int32_t* index, int64_t* count, void* workspace,
+                     int64_t workspace_bytes, void* stream);
+/* dsts[a][r, :] = srcs[a][index[r], :] for r < m, rows of row_bytes[a] bytes (multiples of 4); srcs / dsts / row_bytes
+ * are HOST arrays of num_arrays entries (device pointers inside). */
+int g2pc_gather_rows(const int32_t* index, int64_t m, int32_t num_arrays, const void* const* srcs, void* const* dsts,
+                     const int32_t* row_bytes, void* stream);
+
+/* Magnitudes and point budget without a host round trip: magnitudes[i] (float64) = sqrt(ellipsoid area of Sigma_i,
+ * p = 1.6075) * contrib[i] (gauss_handler.py:252-279, float32 chain, closed-form eigenvalues), ppg[i] (int32) =
+ * round-half-even(magnitude * num_points / sum) with the first min(deficit, #zeros) zero entries raised to 1
+ * (gauss_to_pc.py:73-90; the sum is reduced in a fixed order: bit-identical re-runs). */
+int64_t g2pc_ppg_workspace_bytes(int64_t n);
+int g2pc_points_per_gaussian(const float* cov, const float* contrib, int64_t n, double num_points, double* magnitudes,
+                             int32_t* ppg, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- S3-S6: colour stage, renderer_type=python semantics (gauss_render.py:101-465) ------------------------------ */
 /* Replaces GaussPythonRenderer.__call__/render (gauss_render.py:266-465) and — as the native op boundary — the role
  * of _C.rasterize_gaussians (rasterize_points.cu:36-145) in the per-camera loop of gauss_to_pc.py:437-454.

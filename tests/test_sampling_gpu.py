@@ -157,6 +157,70 @@ def test_distribute_points_matches_oracle(lib, n, num_points):
     assert torch.equal(got, want), f"{int((got != want).sum())} of {n} point counts differ"
 
 
+@pytest.mark.parametrize("n,num_points", [(20000, 200000), (3000, 2000), (50000, 5_000_000)])
+def test_fused_points_per_gaussian(lib, n, num_points):
+    """N1: magnitudes + point budget in one device-side entry point (no host sync) against the torch chain of the drop-in
+    API (get_gaussian_magnitudes + distribute_points, itself checked against the oracle above)."""
+    import gauss_handler as gh
+    import gauss_to_pc as g2p
+    sc, cov0, cov, nrm, mags = _oracle_inputs(n, 1246)
+    d = scene_to(sc, DEV)
+    G = gh.Gaussians(d["xyz"], d["scales"], d["rots"], d["colours"], d["opacities"])
+    G.validate_covariances()
+    contrib = torch.rand(n, device=DEV) * 0.9 + 0.05
+    for c in (None, contrib):
+        ppg, m = G.points_per_gaussian(num_points, c)
+        want_m = G.get_gaussian_magnitudes(c)
+        assert float(((m - want_m).abs() / want_m).max()) < 1e-6, "magnitudes: same f32 chain"
+        want = g2p.distribute_points(m, num_points).to(torch.int32)
+        assert torch.equal(ppg, want), f"{int((ppg != want).sum())} point counts differ"
+        ppg2, _ = G.points_per_gaussian(num_points, c)
+        assert torch.equal(ppg, ppg2)  # fixed-order reduction: bit-identical re-runs
+
+
+def test_fused_cull_matches_mask_chain(lib):
+    """N4: one fused mask + one compaction against the reference-style chain of boolean-index passes."""
+    import gauss_handler as gh
+    n = 50000
+    sc, cov0, cov, nrm, mags = _oracle_inputs(n, 1247)
+    d = scene_to(sc, DEV)
+    g = torch.Generator(device="cpu").manual_seed(9)
+    mc = torch.rand(n, generator=g).to(DEV) * 0.2
+    surf = torch.rand(n, generator=g).to(DEV)
+    extra = (torch.rand(n, generator=g) > 0.1).to(DEV)
+
+    def fresh():
+        G = gh.Gaussians(d["xyz"], d["scales"], d["rots"], d["colours"] * 255, d["opacities"], shs=d["shs"])
+        G.calculate_normals()
+        return G
+    A, B = fresh(), fresh()
+    bmin, bmax = [-1.2, -1.4, -1.3], [1.1, 1.5, 1.25]
+    # reference-style
+    A.add_gaussians_to_cull(surf < 0.8)
+    A.add_gaussians_to_cull(mc > 0.05)
+    A.apply_min_opacity(0.1)
+    A.apply_bounding_box(bmin, bmax)
+    A.add_gaussians_to_cull(extra)
+    keep = A.filter_gaussians()
+    # fused (surface mask + extra through the mask argument, like the pipeline does)
+    idx = B.fused_cull(max_contribution=mc, visibility_threshold=0.05, min_opacity=0.1, bounding_box_min=bmin,
+                       bounding_box_max=bmax, extra_mask=(surf < 0.8) & extra)
+    assert torch.equal(idx, torch.nonzero(keep).squeeze(1))
+    for name in ("xyz", "colours", "opacities", "covariances", "normals", "ids", "scales", "rots", "shs"):
+        assert torch.equal(getattr(A, name), getattr(B, name)), name
+    assert B.filter_indices.shape[0] == idx.shape[0] and bool(B.filter_indices.all())
+    # a second cull composes with the lazily kept arrays; an index shard restricts the rows
+    m2 = mc[idx] > 0.1
+    A.add_gaussians_to_cull(m2)
+    A.filter_gaussians()
+    B.fused_cull(extra_mask=m2)
+    assert torch.equal(A.shs, B.shs) and torch.equal(A.xyz, B.xyz)
+    C = fresh()
+    i3 = C.fused_cull(max_contribution=mc, visibility_threshold=0.05, index_range=(1000, 30000))
+    assert int(i3.min()) >= 1000 and int(i3.max()) < 30000
+    assert torch.equal(i3, torch.nonzero((mc > 0.05) & (torch.arange(n, device=DEV) >= 1000) & (torch.arange(n, device=DEV) < 30000)).squeeze(1))
+
+
 def test_small_std_exact_num_points_replays_instead_of_raising(lib):
     """--mahalanobis_distance_std 0.5 with --exact_num_points needs far more than the first stored attempts
     (acceptance ~3%); the sampler replays the deterministic stream with every attempt stored, like the reference
