@@ -208,7 +208,7 @@ def convert_gaussians_to_pc_sharded(scene, transforms, intrinsics, settings, ren
                                 calculate_surface_distance=s.surface_distance_std is not None)
         names = list(transforms.keys())
         # the accumulate kernel records the index of the camera that raised each maximum (needed by the merge)
-        first_cam = torch.full((n_all,), torch.iinfo(torch.int32).max, dtype=torch.int32, device=keep.device)
+        first_cam = torch.full((n_all,), torch.iinfo(torch.int32).max, dtype=torch.int32, device=scene["xyz"].device)
         renderer.first_frame = first_cam
         renderer.async_mode = True
         for ci in camera_shard(len(names)):
@@ -256,7 +256,8 @@ def convert_gaussians_to_pc_sharded(scene, transforms, intrinsics, settings, ren
     if contributions is not None:
         contributions = contributions[valid]
 
-    mags = gaussians.get_gaussian_magnitudes(contributions=contributions)
+    # the same magnitude kernel as the single-process pipeline (bit-identical magnitudes), then the global budget
+    _, mags = gaussians.points_per_gaussian(s.num_points, contributions)
     ppg = global_points_per_gaussian(mags, s.num_points).to(torch.int32)
     hist = global_histogram(ppg).cpu().numpy()
     bins = sampler.plan_bins(hist, s.exact_num_points)

@@ -20,7 +20,8 @@ from . import capi, config
 
 
 class FrameQueue:
-    """Mixin.  The owner provides: self.device, self._enqueue_front(camera, frame, slot) -> device header tensor,
+    """Mixin.  The owner provides: self.device, self._ensure_buffers(camera, slot) (allocate / grow the slot's scratch on
+    the current stream), self._enqueue_front(camera, frame, slot) -> device header tensor,
     self._enqueue_back(camera, frame, camera_index, slot), self._fix(header_list), self._confirm(header_list) and
     self._reset_counts() (zero the per-slot tile counters after a failure)."""
 
@@ -38,6 +39,10 @@ class FrameQueue:
     def _launch(self, frame, camera, camera_index):
         slot = frame % self.num_slots
         st = self._streams[slot]
+        # every buffer is allocated on the CALLER's stream (never inside the side-stream context): torch's caching
+        # allocator keeps per-stream pools, and a block allocated under a pooled side stream cannot be reused by the next
+        # renderer (different stream objects) — the allocator then falls back to cudaMalloc / cudaFree every step
+        self._ensure_buffers(camera, slot)
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream(self.device))  # inputs prepared on the caller's stream
         st.wait_event(ready)
@@ -92,11 +97,10 @@ class FrameQueue:
         failed = h[capi.HDR_POISON] - 1
         todo = [p for p in self._pending if p[0] >= failed]
         self._pending = [p for p in self._pending if p[0] < failed]
-        with torch.cuda.stream(self._streams[0]):
-            self._fix(h)
-            self._fail.fill_(-1)
-            self._reset_counts()
-        self._streams[0].synchronize()
+        self._fix(h)  # capacities only; the buffers are re-allocated by the next _launch, on the caller's stream
+        self._fail.fill_(-1)
+        self._reset_counts()
+        torch.cuda.current_stream(self.device).synchronize()
         self.replays += 1
         for (frame, camera, cidx, hdr, ev) in todo:
             self._hdr_pool.append(hdr)

@@ -208,14 +208,19 @@ class GaussianRasterizer(FrameQueue):
             raise capi.G2pcError("mask must have image_height * image_width entries")
         return mask.to(torch.int32).contiguous()
 
+    def _ensure_buffers(self, rs, slot):
+        self._pack(float(rs.scale_modifier))
+        t = self._res_tables(int(rs.image_width), int(rs.image_height))
+        self._buffers(t, self._slots[slot])
+        # (kept per slot: the tensor must outlive the frame's kernels, the slot is reused only after they have run)
+        self._slots[slot]["mask"] = self._mask_of(rs, int(rs.image_width), int(rs.image_height))
+
     def _enqueue_front(self, rs, frame, slot):
         st = capi.stream_ptr(self.device)
         W, H = int(rs.image_width), int(rs.image_height)
         n = self._n
-        self._pack(float(rs.scale_modifier))
         t = self._res_tables(W, H)
         sl, ts = self._slots[slot], t["slots"][slot]
-        self._buffers(t, sl)
         c = _raster_struct(rs)
         deg = int(rs.sh_degree) if self._shs_f32 is not None else 0
         capi.call("g2pc_tiles_preprocess", capi.ptr(self._geom), capi.ptr(self._colour_f32), capi.ptr(self._shs_f32),
@@ -239,7 +244,7 @@ class GaussianRasterizer(FrameQueue):
         n = self._n
         t = self._res_tables(W, H)
         sl, ts = self._slots[slot], t["slots"][slot]
-        mask = self._mask_of(rs, W, H)
+        mask = sl.get("mask")
         # pixels that are masked out are never written by the blend (forward.cu:485): they keep the zeros of the fresh
         # output tensors the reference allocates per call (rasterize_points.cu:72-90)
         if mask is not None:

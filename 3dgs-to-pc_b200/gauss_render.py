@@ -211,6 +211,10 @@ class GaussPythonRenderer(FrameQueue):
         if sl["matrix"] is None or sl["matrix"].numel() < mneed:
             sl["matrix"] = torch.empty((max(mneed, 1),), dtype=torch.int32, device=dev)
 
+    def _ensure_buffers(self, camera, slot):
+        t = self._get_tables(int(camera.image_width), int(camera.image_height))
+        self._buffers(t, self._slots[slot])
+
     def _enqueue_front(self, camera, frame, slot):
         """Projection, depth sort, tile table and per-tile lists of one camera, asynchronously on the current stream."""
         st = capi.stream_ptr(self.device)
@@ -220,7 +224,6 @@ class GaussPythonRenderer(FrameQueue):
         t = self._get_tables(W, H)
         qt = t["qt"]
         sl, ts = self._slots[slot], t["slots"][slot]
-        self._buffers(t, sl)
         capi.call("g2pc_preprocess", capi.ptr(self._geom), capi.ptr(self._colour_f32) if self.shs is None else None,
                   capi.ptr(self.shs), int(self.shs.shape[-1]) if self.shs is not None else 0, self.sh_degree, n,
                   ctypes.byref(cam), capi.ptr(t["tables"]), capi.ptr(t["luts"]), qt.num_levels, t["level_mask"],

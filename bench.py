@@ -223,8 +223,15 @@ def run_ours(args):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         pc = None
+        dbg = os.environ.get("G2PC_BENCH_DEBUG")
         for _ in range(steps):
+            t0 = time.perf_counter()
             pc = fn()
+            if dbg:
+                t1 = time.perf_counter()
+                torch.cuda.synchronize()
+                print(f"[rank {rank}] {fn.__name__}: host {1e3 * (t1 - t0):.1f} ms, +drain {1e3 * (time.perf_counter() - t1):.1f} ms",
+                      file=sys.stderr, flush=True)
         b.record()
         barrier()
         ms = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)

@@ -55,4 +55,5 @@ if rank == 0:
         print("DIST_CHECK_OK")
 dist.barrier()
 dist.destroy_process_group()
+sys.stdout.flush()
 sys.exit(0 if ok else 1)

@@ -119,9 +119,15 @@ def test_generate_pointcloud_parity(lib, n, num_points, exact, attempts, cull_mo
             pass  # different accept test than the oracle's explicit one: only ambiguous samples may differ
         if bad.size:
             # every mismatching Gaussian must own a sample within the fp32 conditioning bound of the threshold
+            # the fp32 distance of a sample is only good to ~cond(Sigma) * eps: LAPACK's LU inverse (oracle / reference)
+            # and the kernel's adjugate inverse differ by up to 1e-2 relative on the worst-conditioned splats
+            # (SURVEY.md §3.4 probe: 8.6e-7 median, 3.6e-5 p99, 1e-2 max on cond up to 2e6)
+            ev = np.linalg.eigvalsh(cov[idx].double().numpy())
+            cond = ev[:, -1] / np.maximum(ev[:, 0], 1e-300)
+            band = np.where(cond > 1e4, 2e-2, 2e-3) * 2.0
             amb = np.zeros(cnt, dtype=bool)
             for (todo, dmat) in dists:
-                near = (np.abs(dmat - 2.0) < 2e-3 * 2.0).any(axis=1)
+                near = (np.abs(dmat - 2.0) < band[todo][:, None]).any(axis=1)
                 amb[todo[near]] = True
             assert amb[bad].all(), f"bin {b}: count mismatch not explained by a threshold-ambiguous sample"
             n_mismatch += bad.size
