@@ -568,10 +568,15 @@ extern "C" int g2pc_depth_sort(const uint32_t* depth_key, const uint64_t* val, i
 }
 
 extern "C" int32_t g2pc_multisplit_chunk(int32_t leaf_cap) {
-    // entries per chunk: the scatter kernel keeps leaf_cap x chunk bits in shared memory
-    if ((int64_t)leaf_cap * 36 <= 160 * 1024) return 256;
-    if ((int64_t)leaf_cap * 20 <= 160 * 1024) return 128;
-    if ((int64_t)leaf_cap * 12 <= 160 * 1024) return 64;
+    // entries per chunk: the scatter kernel keeps leaf_cap x (chunk bits + one offset) in shared memory.  Prefer a
+    // footprint that lets 3 CTAs share an SM (the kernel is a chain of short latency-bound phases: with one resident CTA
+    // per SM the 3600-tile grid of the CUDA back-end ran 3.5x slower per instance than the 1024 leaves of the python one)
+    const int64_t n = leaf_cap;
+    if (n * 36 <= 74 * 1024) return 256;
+    if (n * 20 <= 74 * 1024) return 128;
+    if (n * 12 <= 110 * 1024) return 64;
+    if (n * 20 <= 200 * 1024) return 128;
+    if (n * 12 <= 200 * 1024) return 64;
     return 0;
 }
 

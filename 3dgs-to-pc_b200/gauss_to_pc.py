@@ -15,6 +15,7 @@ from gauss_handler import Gaussians
 from gauss_render import get_renderer
 from camera_handler import get_camera
 from g2pc import capi, config, sampler
+from g2pc.trace import nvtx
 
 LAST_SAMPLE_STATS = {}
 LAST_RENDER_STATS = {}
@@ -271,10 +272,11 @@ def convert_gaussians_to_pc(xyz, scales, rots, colours, opacities, shs, transfor
     s = pointcloud_settings
     say = (lambda *a: None) if s.quiet else print
 
-    gaussians = Gaussians(xyz, scales, rots, colours, opacities, shs=shs)
+    with nvtx("g2pc: covariances + normals"):
+        gaussians = Gaussians(xyz, scales, rots, colours, opacities, shs=shs)
 
-    if s.calculate_normals:
-        gaussians.calculate_normals()
+        if s.calculate_normals:
+            gaussians.calculate_normals()
 
     total_gaussian_contributions = None
 
@@ -303,7 +305,8 @@ def convert_gaussians_to_pc(xyz, scales, rots, colours, opacities, shs, transfor
                 mask = mask_images[img_name].to(s.device)
             camera = get_camera(s.renderer_type, transform, intrinsics[img_name], colour_resolution=s.colour_resolution,
                                 sh_degree=s.max_sh_degree, white_bkgd=True, mask=mask)
-            render, _, _, depth_map = gaussian_renderer(camera)
+            with nvtx(f"g2pc: camera {img_name}"):
+                render, _, _, depth_map = gaussian_renderer(camera)
 
         say(f"\nNumber Initial Gaussians: {gaussians.xyz.shape[0]}")
 
@@ -343,7 +346,8 @@ def convert_gaussians_to_pc(xyz, scales, rots, colours, opacities, shs, transfor
 
     say("\nEnsuring Gaussians are Positive Semidefinite")
 
-    valid = gaussians.validate_covariances()
+    with nvtx("g2pc: validate covariances"):
+        valid = gaussians.validate_covariances()
 
     if total_gaussian_contributions is not None:
         total_gaussian_contributions = total_gaussian_contributions[valid]
@@ -352,12 +356,13 @@ def convert_gaussians_to_pc(xyz, scales, rots, colours, opacities, shs, transfor
 
     say("\nStarting Point Cloud Generation for All Gaussians\n")
 
-    points, colours, normals = generate_pointcloud(gaussians, s.num_points, exact_num_points=s.exact_num_points,
-                                                   mahalanobis_distance_std=s.mahalanobis_distance_std,
-                                                   calculate_normals=s.calculate_normals,
-                                                   num_sample_attempts=num_sample_attempts,
-                                                   contributions=total_gaussian_contributions,
-                                                   device=s.device, quiet=s.quiet)
+    with nvtx("g2pc: point budget + sampling"):
+        points, colours, normals = generate_pointcloud(gaussians, s.num_points, exact_num_points=s.exact_num_points,
+                                                       mahalanobis_distance_std=s.mahalanobis_distance_std,
+                                                       calculate_normals=s.calculate_normals,
+                                                       num_sample_attempts=num_sample_attempts,
+                                                       contributions=total_gaussian_contributions,
+                                                       device=s.device, quiet=s.quiet)
 
     total_point_cloud = PointCloudData(points=points, colours=colours, normals=normals)
     surface_point_cloud = None
