@@ -54,6 +54,7 @@ struct BlendParams {
     float t_stop;
     int32_t* work_counter;  // cleared by the tree kernel: dynamic (leaf, slab) work distribution
     int32_t slabs;
+    int32_t compact;        // 1: compact warp footprints (blocks), 0: row strips
     unsigned long long* stats;
 };
 
@@ -128,13 +129,33 @@ __global__ void __launch_bounds__(BT, 8) blend_kernel(const BlendParams p) {
     if (item >= num_items) break;
     const g2pc_leaf_t lf = p.leaves[p.leaf_order[item / p.slabs]];
     const int qpr = (lf.w + 3) >> 2;
-    const int nquads = qpr * lf.h;
-    const int quad0 = (item % p.slabs) * BT;
-    if (quad0 >= nquads) continue;
-    const int quad = quad0 + tid;
-    const bool active = quad < nquads;
-    const int row = active ? quad / qpr : 0;
-    const int x0 = active ? (quad - row * qpr) * 4 : 0;
+    bool active;
+    int row, x0;
+    if (p.compact) {
+        // compact warp footprints: a warp owns a block of tw quad columns x th rows (<= 32 quads, e.g. 20 x 6 pixels of a
+        // 40 x 23 leaf) instead of a strip of full rows — the pixels of a block reach the transmittance stop together
+        const int ncb = (qpr + 4) / 5;                 // blocks across
+        const int tw = (qpr + ncb - 1) / ncb;          // <= 5 quad columns per block
+        const int th = 32 / tw;                        // rows per block
+        const int nrb = (lf.h + th - 1) / th;
+        const int wblock = (item % p.slabs) * (BT / 32) + warp;   // block of this warp
+        if ((item % p.slabs) * (BT / 32) >= ncb * nrb) continue;  // uniform: no block left for this slab
+        const int bx = wblock % ncb, by = wblock / ncb;
+        const int lr = lane / tw, lc = lane - lr * tw;
+        row = by * th + lr;
+        const int qc = bx * tw + lc;
+        active = wblock < ncb * nrb && lr < th && row < lf.h && qc < qpr;
+        x0 = qc * 4;
+        if (!active) { row = 0; x0 = 0; }
+    } else {
+        const int nquads = qpr * lf.h;
+        const int quad0 = (item % p.slabs) * BT;
+        if (quad0 >= nquads) continue;
+        const int quad = quad0 + tid;
+        active = quad < nquads;
+        row = active ? quad / qpr : 0;
+        x0 = active ? (quad - row * qpr) * 4 : 0;
+    }
 
     // two pixel pairs per thread: Blackwell's packed FP32x2 pipe (FADD2 / FMUL2 / FFMA2) takes a scalar broadcast operand,
     // so the per-Gaussian scalars feed both pixels of a pair without extra moves
@@ -331,6 +352,10 @@ __global__ void __launch_bounds__(256) compose_kernel(uint32_t* __restrict__ own
 
 }  // namespace
 
+static int g_blend_compact = 1;
+/* experiment switch (bench / tests): 1 = compact warp footprints (default), 0 = row strips */
+extern "C" void g2pc_blend_set_compact(int on) { g_blend_compact = on ? 1 : 0; }
+
 extern "C" int g2pc_blend(const g2pc_leaf_t* leaves, const int32_t* leaf_order, const int32_t* header,
                           const uint32_t* fail, int32_t frame, int32_t max_leaf_pixels_quads, const uint32_t* inst_gid,
                           const void* proj,
@@ -350,7 +375,10 @@ extern "C" int g2pc_blend(const g2pc_leaf_t* leaves, const int32_t* leaf_order, 
     p.owner = owner;
     p.W = width; p.H = height; p.bg = background;
     p.t_stop = t_stop > 1.17549435e-38f ? t_stop : 1.17549435e-38f;
-    p.slabs = (max_leaf_pixels_quads + BT - 1) / BT;
+    p.compact = g_blend_compact;
+    // slabs: CTAs per leaf.  Row strips: ceil(quads / 128).  Blocks: a leaf of max_tile_size has at most
+    // ceil(qpr / 5) x ceil(h / 6) blocks of <= 32 quads; the caller's bound is quads = ceil(w / 4) * h <= 15 * h.
+    p.slabs = p.compact ? (max_leaf_pixels_quads + 4 * 25 - 1) / (4 * 25) + 1 : (max_leaf_pixels_quads + BT - 1) / BT;
     p.work_counter = work_counters;
     p.stats = (unsigned long long*)stats;
     static int resident = 0;  // persistent grid: every SM filled to the kernel's occupancy (device constant)

@@ -54,6 +54,7 @@ SIGNATURES = {
                          _c_void_p, _c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
     "g2pc_blend": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _i32, _i32, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                     _c_void_p, _c_void_p, _i32, _i32, _f32, _f32, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
+    "g2pc_blend_set_compact": ([ctypes.c_int], None),
     "g2pc_accumulate": ([_c_void_p, _c_void_p, _i64, _c_void_p, _c_void_p, _c_void_p, _i32, _c_void_p], ctypes.c_int),
     "g2pc_tiles_preprocess": ([_c_void_p, _c_void_p, _c_void_p, _i32, _i32, _i32, _i64, _c_void_p, _c_void_p, _c_void_p,
                                _c_void_p, _c_void_p, _c_void_p, _c_void_p], ctypes.c_int),
@@ -124,7 +125,7 @@ TIMING = None     # None, or a dict filled as {entry point name: [(start_event, 
 _OWN_KERNELS = {"g2pc_multisplit": 5, "g2pc_multisplit_grid": 5, "g2pc_depth_sort": 0, "g2pc_cull_select": 3,
                 "g2pc_points_per_gaussian": 5}
 _NOT_KERNELS = {"g2pc_version", "g2pc_last_error", "g2pc_sample_emit_chunk_points", "g2pc_multisplit_chunk",
-                "g2pc_multisplit_rows", "g2pc_cull_workspace_bytes", "g2pc_ppg_workspace_bytes",
+                "g2pc_multisplit_rows", "g2pc_blend_set_compact", "g2pc_cull_workspace_bytes", "g2pc_ppg_workspace_bytes",
                 "g2pc_depth_sort_workspace_bytes"}
 
 

@@ -64,6 +64,7 @@ def parse():
     ap.add_argument("--renderer", default=None, choices=["python", "cuda"],
                     help="colour back-end semantics (default: the workload's, python unless stated)")
     ap.add_argument("--strict-blend", action="store_true", help="t_stop = FLT_MIN (strict-parity blend)")
+    ap.add_argument("--blend-strips", action="store_true", help="row-strip pixel mapping in the blend (default: compact blocks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-c1", action="store_true")
@@ -163,6 +164,8 @@ def run_ours(args):
     wl = WORKLOADS[args.workload]
     if args.strict_blend:
         config.BLEND_T_STOP = 0.0
+    if args.blend_strips:
+        capi.load().g2pc_blend_set_compact(0)
     st = settings_for(wl, g2p, dev, args.renderer)
 
     sc = _scene_for(wl)

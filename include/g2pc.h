@@ -270,6 +270,10 @@ int g2pc_blend(const g2pc_leaf_t* leaves, const int32_t* leaf_order, const int32
                const float* max_contrib, float* leaf_colour, uint32_t* owner, int32_t width, int32_t height,
                float background, float t_stop, int32_t* work_counters, uint64_t* stats, void* stream);
 
+/* Pixel-to-thread mapping of g2pc_blend: 1 (default) = a warp owns a compact block of <= 32 quads (e.g. 20 x 6 pixels),
+ * 0 = a warp owns a strip of full rows.  Results do not depend on it up to the t_stop tolerance. */
+void g2pc_blend_set_compact(int on);
+
 /* S6.  Fold one camera into the per-Gaussian accumulators (gauss_render.py:387-395; the role of
  * GaussianRasterizer.update_max_contributions, gaussian_pointcloud_rasterization/__init__.py:142-152):
  * where the camera's best contribution beats max_contrib[g] (strict >) store it and the blended colour of the winning
