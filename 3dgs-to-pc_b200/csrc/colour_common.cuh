@@ -109,7 +109,9 @@ __device__ __forceinline__ bool axis_member(const int32_t* __restrict__ s, const
 // walked by the whole warp — the lanes tile the rectangle with a power-of-two number of columns, so no division is
 // needed — otherwise the warp runs at the speed of its largest rectangle (ncu r02a: 6.9 of 32 threads active in the
 // multisplit).  Must be called by all 32 lanes.
-constexpr int WARP_SMALL_AREA = 4;
+// (a cooperative iteration costs ~45 instructions of shuffles / loop control, a private node ~12: the break-even rectangle
+// is ~10 nodes; with a threshold of 4 the typical 2x3 / 3x3 rectangles all went the slow cooperative way)
+constexpr int WARP_SMALL_AREA = 12;
 template <typename F>
 __device__ __forceinline__ void warp_for_each_node(uint32_t range, uint32_t payload, F f) {
     const int lane = threadIdx.x & 31;
