@@ -258,9 +258,20 @@ __global__ void __launch_bounds__(256, 4) preprocess_kernel(const PreParams p) {
             const int xlo = L[qx0], xhi = (int)L[p.cam.width + cx1] - 1;
             const int ylo = L[2 * p.cam.width + qy0], yhi = (int)L[2 * p.cam.width + p.cam.height + cy1] - 1;
             if (xlo > xhi || ylo > yhi) continue;
+            if (use_hist && ((p.clean_mask >> l) & 1u)) {
+                // the common case, kept branch-light: shared-memory flags, no per-node table checks, and almost always a
+                // single node (one predicated store)
+                uint32_t* f = s_hist + off2(l);
+                if (xlo == xhi && ylo == yhi) {
+                    f[(ylo << l) + xlo] = 1u;
+                } else {
+                    for (int iy = ylo; iy <= yhi; ++iy)
+                        for (int ix = xlo; ix <= xhi; ++ix) f[(iy << l) + ix] = 1u;
+                }
+                continue;
+            }
             uint32_t* flags = (use_hist ? s_hist : p.node_cnt) + off2(l);
             if ((p.clean_mask >> l) & 1u) {
-                // (almost always a single node)
                 for (int iy = ylo; iy <= yhi; ++iy)
                     for (int ix = xlo; ix <= xhi; ++ix) flags[(iy << l) + ix] = 1u;
                 continue;
