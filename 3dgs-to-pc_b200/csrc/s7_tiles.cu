@@ -8,8 +8,11 @@
 //   rasterizer_impl.cu:69-137,285-326        duplicateWithKeys / radix sort / identifyTileRanges  -> per-tile depth-ordered lists
 //   forward.cu:303-497      renderCUDA       (blend, max contribution :434-456, surface distance :460-477, mask :334,389,485)
 //   gaussian_pointcloud_rasterization/__init__.py:126-158   per-camera accumulator updates
-// Nothing of their structure is kept: the per-tile lists come from the same depth sort + bit-matrix multisplit as the
-// python-semantics path (s4_tree.cu: a tile is a "leaf", leaf index = tile index, the packed node range is the tile rect),
+// Nothing of their structure is kept: the depth-ordered lists come from the same depth sort + bit-matrix multisplit as the
+// python-semantics path (s4_tree.cu), built per SUPER-TILE of 2x2 tiles (32x32 pixels: 900 lists at 1280x720 instead of
+// 3600 — the multisplit's cost grows with the number of lists); the blend of a tile walks its super-tile's list and skips
+// the entries whose tile rect (packed into the projection record) does not contain the tile, so every tile still sees
+// exactly its own list, in order, and the 256-entry rounds of the surface distance count the tile's own entries;
 // the blend is a persistent kernel with TMA-staged id chunks, cp.async record gathers and packed FP32x2 arithmetic, and
 // every cross-thread reduction is a deterministic max / min (the reference's shared-memory CAS loop, its racing
 // `largest_collected_contribution_pixel` store and its non-atomic cross-block updates make its results run-dependent —
@@ -32,9 +35,9 @@ struct TilePreParams {
     int64_t n;
     float view[16], projm[16], campos[3];
     float tan_fovx, tan_fovy, focal_x, focal_y;
-    int32_t W, H, gx, gy;
+    int32_t W, H, gx, gy, sgx, sgy;  // tile grid, super-tile grid
     float4* proj;
-    uint32_t* node_cnt;    // per tile
+    uint32_t* node_cnt;    // per super-tile
     uint32_t* depth_key;
     unsigned long long* val;
     int32_t* radii;        // (n) int32 or null
@@ -74,7 +77,7 @@ __device__ __forceinline__ float3 sh_eval(const float* __restrict__ sh, int stri
 
 __global__ void __launch_bounds__(256) preprocess_tiles_kernel(const TilePreParams p) {
     extern __shared__ uint32_t s_hist_t[];
-    const int ntiles = p.gx * p.gy;
+    const int ntiles = p.sgx * p.sgy;
     if (p.use_hist) {
         for (int k = threadIdx.x; k < ntiles; k += blockDim.x) s_hist_t[k] = 0u;
         __syncthreads();
@@ -156,16 +159,18 @@ __global__ void __launch_bounds__(256) preprocess_tiles_kernel(const TilePrePara
                     const float K = -0.72134752044448170368f;  // -0.5 log2(e)
                     q0 = make_float4(pix_x, pix_y, kx * K, 2.0f * ky * K);
                     q1 = make_float4(kz * K, g2.y, rgb.x, rgb.y);
-                    q2 = make_float4(rgb.z, vz, my_radius, 1.0f);
+                    // q2.w carries the packed TILE rect (the blend's membership filter)
+                    q2 = make_float4(rgb.z, vz, my_radius,
+                                     __uint_as_float(g2pc_pack_range(rx0, rx1 - 1, ry0, ry1 - 1)));
                     radius_out = ir;
-                    range = g2pc_pack_range(rx0, rx1 - 1, ry0, ry1 - 1);
+                    range = g2pc_pack_range(rx0 >> 1, (rx1 - 1) >> 1, ry0 >> 1, (ry1 - 1) >> 1);  // super-tiles
                 }
             }
         }
         // Gaussians per tile; large rects are walked by the whole warp (all 32 lanes reach this point)
         warp_for_each_node(range, 0u, [&](int tx_, int ty_, int, uint32_t) {
-                               if (p.use_hist) atomicAdd(s_hist_t + ty_ * p.gx + tx_, 1u);
-                               else atomicAdd(p.node_cnt + ty_ * p.gx + tx_, 1u);
+                               if (p.use_hist) atomicAdd(s_hist_t + ty_ * p.sgx + tx_, 1u);
+                               else atomicAdd(p.node_cnt + ty_ * p.sgx + tx_, 1u);
                            });
         if (i < p.n) {
             float4* rec = p.proj + 3 * i;
@@ -237,7 +242,7 @@ __global__ void __launch_bounds__(TB) tile_tree_kernel(const TileTreeParams p) {
         if (threadIdx.x == 0) { p.header[G2PC_HDR_POISON] = (int32_t)*p.fail; p.header[G2PC_HDR_FRAME] = p.frame; }
         return;
     }
-    const int nt = p.gx * p.gy;
+    const int nt = p.gx * p.gy;  // (gx, gy = super-tile grid here)
     const int nl = nt < p.max_leaves ? nt : p.max_leaves;
     long long inst_total = 0;
     for (int k0 = 0; k0 < nl; k0 += TB) {
@@ -249,8 +254,8 @@ __global__ void __launch_bounds__(TB) tile_tree_kernel(const TileTreeParams p) {
         if (i < nl) {
             const int ty = i / p.gx, tx = i - ty * p.gx;
             g2pc_leaf_t lf;
-            lf.r0 = ty * TILE; lf.c0 = tx * TILE;
-            lf.w = min(TILE, p.W - lf.c0); lf.h = min(TILE, p.H - lf.r0);
+            lf.r0 = ty * 2 * TILE; lf.c0 = tx * 2 * TILE;
+            lf.w = min(2 * TILE, p.W - lf.c0); lf.h = min(2 * TILE, p.H - lf.r0);
             lf.inst_begin = (int32_t)(inst_total + pc);
             lf.inst_count = cnt;
             lf.pix_offset = 0;
@@ -308,9 +313,13 @@ __global__ void __launch_bounds__(TB) tile_tree_kernel(const TileTreeParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Blend: one 16x16 tile per work item, 64 threads x 4 pixels (a row quad each), chunks of 128 list entries through the same
-// 3-deep pipeline as s5_blend.cu (TMA bulk copy of the ids, cp.async gather of the records, blend).
-constexpr int TBT = 64;
+// Blend: one super-tile (2x2 tiles of 16x16 pixels) per work item, 256 threads: tile s = warps 2s, 2s+1, a thread blends a
+// row quad of its tile.  Chunks of 128 list entries go through the same 3-deep pipeline as s5_blend.cu (TMA bulk copy of
+// the ids, cp.async gather of the records, blend); the records are fetched once per super-tile and every tile skips the
+// entries whose tile rect does not contain it (a warp-uniform branch), so each tile blends exactly its own depth-ordered
+// list.  The surface-distance rounds (256 entries of the TILE's list) are counted per tile and flushed with a 64-thread
+// named barrier.
+constexpr int TBT = 256;
 constexpr int TCH = 128;
 
 struct TileBlendParams {
@@ -366,27 +375,39 @@ __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_gro
 template <int N>
 __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+__device__ __forceinline__ void pair_sync(int tile) {  // the two warps of one tile (static ids: a register id makes
+    switch (tile) {                                     // ptxas reserve all 16 barriers and caps the CTAs per SM)
+        case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+        case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+        default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    }
+}
+
 template <bool SURF>
-__global__ void __launch_bounds__(TBT, 12) blend_tiles_kernel(const TileBlendParams p) {
+__global__ void __launch_bounds__(TBT, SURF ? 3 : 4) blend_tiles_kernel(const TileBlendParams p) {
     __shared__ __align__(16) float4 s_q0[2][TCH];
     __shared__ __align__(16) float4 s_q1[2][TCH];
-    __shared__ __align__(16) float4 s_q2[2][TCH];  // (blue, depth, radius, valid)
+    __shared__ __align__(16) float4 s_q2[2][TCH];  // (blue, depth, radius, packed tile rect)
     __shared__ __align__(16) uint32_t s_gid[3][TCH];
     __shared__ unsigned long long s_best[TBT / 32][TCH];
     __shared__ __align__(8) unsigned long long s_bar[3];
     __shared__ int s_item;
-    __shared__ float s_E[SURF ? 256 : 1];         // running expected depths of the tile's threads, sorted per round
-    __shared__ float s_rdepth[SURF ? 256 : 1];    // depths / ids of the current round's entries
-    __shared__ uint32_t s_rgid[SURF ? 256 : 1];
+    __shared__ float s_E[SURF ? 4 : 1][SURF ? 256 : 1];       // expected depths of a tile's threads, sorted per round
+    __shared__ float s_rdepth[SURF ? 4 : 1][SURF ? 256 : 1];  // depths / ids of the tile's current round
+    __shared__ uint32_t s_rgid[SURF ? 4 : 1][SURF ? 256 : 1];
+    __shared__ int s_pair_live[SURF ? 4 : 1][2];
 
     if (g2pc_frame_skipped(p.fail, p.frame)) return;
     const int num_items = p.header[G2PC_HDR_NUM_LEAVES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = tid >> 6, tt = tid & 63;  // tile of the super-tile, thread of the tile
     if (tid == 0) {
         mb_init(&s_bar[0], 1); mb_init(&s_bar[1], 1); mb_init(&s_bar[2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int w = 0; w < TBT / 32; ++w) { s_best[w][tid] = 0ull; s_best[w][tid + TBT] = 0ull; }
+    for (int w = 0; w < TBT / 32; ++w)
+        for (int t = tid; t < TCH; t += TBT) s_best[w][t] = 0ull;
     uint32_t phase_bits = 0;
     unsigned long long iters = 0;
     __syncthreads();
@@ -398,25 +419,28 @@ __global__ void __launch_bounds__(TBT, 12) blend_tiles_kernel(const TileBlendPar
     __syncthreads();
     if (item >= num_items) break;
     const g2pc_leaf_t lf = p.leaves[p.leaf_order[item]];
-    const int row = tid >> 2, x0 = (tid & 3) * 4;
-    const int gy_ = lf.r0 + row;
-    const bool row_in = row < lf.h;
+    const int tc0 = lf.c0 + (tile & 1) * TILE, tr0 = lf.r0 + (tile >> 1) * TILE;  // the tile's origin
+    const int tw = max(0, min(TILE, p.W - tc0)), th = max(0, min(TILE, p.H - tr0));
+    const uint32_t tix = (uint32_t)(tc0 / TILE), tiy = (uint32_t)(tr0 / TILE);
+    const int row = tt >> 2, x0 = (tt & 3) * 4;
+    const int gy_ = tr0 + row;
+    const bool row_in = row < th;
     // per pixel: inside the image and not masked out -> live; `live` drops to 0 when the pixel stops (T would fall below 1e-4)
     float live[4], T[4], Cr[4], Cg[4], Cb[4], D[4], ID[4], px[4];
     bool valid[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const bool inside = row_in && (x0 + i < lf.w);
+        const bool inside = row_in && (x0 + i < tw);
         bool m = inside;
-        if (inside && p.mask) m = p.mask[(int64_t)gy_ * p.W + lf.c0 + x0 + i] != 0;
+        if (inside && p.mask) m = p.mask[(int64_t)gy_ * p.W + tc0 + x0 + i] != 0;
         valid[i] = m;
         live[i] = m ? 1.0f : 0.0f;
         T[i] = 1.0f; Cr[i] = Cg[i] = Cb[i] = D[i] = ID[i] = 0.0f;
-        px[i] = (float)(lf.c0 + x0 + i);
+        px[i] = (float)(tc0 + x0 + i);
     }
     const float py = (float)gy_;
-    const int pix_base = gy_ * p.W + lf.c0 + x0;
-    const bool tile_has_outside = (lf.w < TILE) || (lf.h < TILE);
+    const int pix_base = gy_ * p.W + tc0 + x0;
+    const bool tile_has_outside = (tw < TILE) || (th < TILE);
 
     const int cnt = lf.inst_count;
     const int nchunks = (cnt + TCH - 1) / TCH;
@@ -433,16 +457,50 @@ __global__ void __launch_bounds__(TBT, 12) blend_tiles_kernel(const TileBlendPar
     };
     auto issue_records = [&](int c) {
         const int nl = min(TCH, cnt - c * TCH);
-        for (int t = tid; t < nl; t += TBT) {
-            const float4* rec = p.proj + 3 * (int64_t)s_gid[c % 3][t];
-            cpa16(&s_q0[c & 1][t], rec);
-            cpa16(&s_q1[c & 1][t], rec + 1);
-            cpa16(&s_q2[c & 1][t], rec + 2);
+        if (tid < nl) {
+            const float4* rec = p.proj + 3 * (int64_t)s_gid[c % 3][tid];
+            cpa16(&s_q0[c & 1][tid], rec);
+            cpa16(&s_q1[c & 1][tid], rec + 1);
+            cpa16(&s_q2[c & 1][tid], rec + 2);
         }
         cpa_commit();
     };
+    // end of a round of the tile's list (forward.cu:460-477): distance of every entry of the round to the nearest running
+    // expected depth among the tile's 256 threads.  Sort the values once, then binary-search per entry.  Both warps of
+    // the tile call this at the same entry.
+    auto flush_round = [&](int nround) {
+        float* E = s_E[SURF ? tile : 0];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) E[tt * 4 + i] = valid[i] ? D[i] : 3.0e38f;
+        pair_sync(tile);
+        for (int k = 2; k <= 256; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tt; i < 256; i += 64) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const float a = E[i], b = E[ixj];
+                        const bool up = (i & k) == 0;
+                        if ((a > b) == up) { E[i] = b; E[ixj] = a; }
+                    }
+                }
+                pair_sync(tile);
+            }
+        for (int t = tt; t < nround; t += 64) {
+            const float d = s_rdepth[SURF ? tile : 0][t];
+            int lo = 0, hi = 256;  // first index with E >= d
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (E[mid] < d) lo = mid + 1; else hi = mid; }
+            float best = 3.0e38f;
+            if (lo < 256 && E[lo] < 1.0e38f) best = fabsf(E[lo] - d);
+            if (lo > 0 && E[lo - 1] < 1.0e38f) best = fminf(best, fabsf(d - E[lo - 1]));
+            if (tile_has_outside) best = fminf(best, fabsf(d));  // threads outside the image hold expected depth 0
+            if (best < 1.0e38f) atomicMin(p.cam_dist + s_rgid[SURF ? tile : 0][t], __float_as_uint(best));
+        }
+        pair_sync(tile);
+    };
 
-    bool warp_done = false;
+    bool warp_done = false;   // no live pixel left in this warp
+    bool tile_left = (tw == 0) || (th == 0);  // the tile has left its list (or lies outside the image)
+    int members = 0;          // entries of the tile's own list seen so far
     if (nchunks > 0) {
         if (tid == 0) { issue_ids(0); if (nchunks > 1) issue_ids(1); }
         wait_ids(0);
@@ -453,9 +511,8 @@ __global__ void __launch_bounds__(TBT, 12) blend_tiles_kernel(const TileBlendPar
         const bool more = (c + 1 < nchunks);
         if (more) { wait_ids(c + 1); issue_records(c + 1); }
         if (more) cpa_wait<1>(); else cpa_wait<0>();
-        const bool all_done = __syncthreads_and(warp_done ? 1 : 0);
-        // the reference leaves a tile when every thread is done at the START of a 256-entry round (forward.cu:366-369)
-        if (all_done && (!SURF || (c & 1) == 0)) {
+        const bool all_left = __syncthreads_and((SURF ? tile_left : (tile_left || warp_done)) ? 1 : 0);
+        if (all_left) {
             if (more) cpa_wait<0>();
             break;
         }
@@ -463,52 +520,82 @@ __global__ void __launch_bounds__(TBT, 12) blend_tiles_kernel(const TileBlendPar
         const float4* q0s = s_q0[c & 1];
         const float4* q1s = s_q1[c & 1];
         const float4* q2s = s_q2[c & 1];
-        if (!warp_done) {
+        const uint32_t* gids = s_gid[c % 3];
+        if (SURF ? !tile_left : !(tile_left || warp_done)) {
             for (int j = 0; j < nload; ++j) {
-                const float4 q0 = q0s[j];
-                const float4 q1 = q1s[j];
                 const float4 q2 = q2s[j];
-                const float dy = py - q0.y;
-                const float Bq = dy * q0.w;
-                const float Cq = dy * dy * q1.x;           // power' without the opacity term
-                const float depth = q2.y, idepth = 1.0f / q2.y;
-                float c4[4];
+                const uint32_t rect = __float_as_uint(q2.w);
+                // the tile's own list = the entries whose tile rect contains it (warp-uniform)
+                if (tix - (rect & 255u) > ((rect >> 8) & 255u) - (rect & 255u) ||
+                    tiy - ((rect >> 16) & 255u) > (rect >> 24) - ((rect >> 16) & 255u))
+                    continue;
+                if (SURF) {
+                    // the reference leaves a tile when all its threads are done at the START of a round (forward.cu:366-369)
+                    if ((members & 255) == 0 && members > 0) {
+                        const float lmax = fmaxf(fmaxf(live[0], live[1]), fmaxf(live[2], live[3]));
+                        const bool warp_live = __any_sync(FULLM, lmax != 0.0f);
+                        if (lane == 0) s_pair_live[tile][warp & 1] = warp_live ? 1 : 0;
+                        pair_sync(tile);
+                        const bool any_live = (s_pair_live[tile][0] | s_pair_live[tile][1]) != 0;
+                        pair_sync(tile);
+                        if (!any_live) { tile_left = true; break; }
+                    }
+                    if ((warp & 1) == 0 && lane == 0) {
+                        s_rdepth[tile][members & 255] = q2.y;
+                        s_rgid[tile][members & 255] = gids[j];
+                    }
+                }
+                ++members;
+                if (!warp_done) {
+                    const float4 q0 = q0s[j];
+                    const float4 q1 = q1s[j];
+                    const float dy = py - q0.y;
+                    const float Bq = dy * q0.w;
+                    const float Cq = dy * dy * q1.x;           // power' without the opacity term
+                    const float depth = q2.y, idepth = 1.0f / q2.y;
+                    float c4[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float dx = px[i] - q0.x;
-                    const float pw = fmaf(dx, fmaf(dx, q0.z, Bq), Cq);  // = power * log2(e)
-                    const float alpha = fminf(0.99f, ex2a(pw + q1.y));
-                    // power > 0 -> skip; alpha < 1/255 -> skip (forward.cu:404,412)
-                    const bool keep = !(pw > 0.0f) && !(alpha < (1.0f / 255.0f));
-                    const float cand = T[i] * alpha;
-                    const float testT = T[i] * (1.0f - alpha);
-                    // the pixel stops BEFORE taking a contribution that would leave T < 1e-4 (forward.cu:414-419)
-                    if (keep && testT < 0.0001f) live[i] = 0.0f;
-                    const float c = (keep ? cand : 0.0f) * live[i];
-                    const bool take = keep && (live[i] != 0.0f);
-                    T[i] = take ? testT : T[i];
-                    Cr[i] = fmaf(c, q1.z, Cr[i]);
-                    Cg[i] = fmaf(c, q1.w, Cg[i]);
-                    Cb[i] = fmaf(c, q2.x, Cb[i]);
-                    D[i] = fmaf(c, depth, D[i]);
-                    ID[i] = fmaf(c, idepth, ID[i]);
-                    c4[i] = c;
+                    for (int i = 0; i < 4; ++i) {
+                        const float dx = px[i] - q0.x;
+                        const float pw = fmaf(dx, fmaf(dx, q0.z, Bq), Cq);  // = power * log2(e)
+                        const float alpha = fminf(0.99f, ex2a(pw + q1.y));
+                        // power > 0 -> skip; alpha < 1/255 -> skip (forward.cu:404,412)
+                        const bool keep = !(pw > 0.0f) && !(alpha < (1.0f / 255.0f));
+                        const float cand = T[i] * alpha;
+                        const float testT = T[i] * (1.0f - alpha);
+                        // the pixel stops BEFORE taking a contribution that would leave T < 1e-4 (forward.cu:414-419)
+                        if (keep && testT < 0.0001f) live[i] = 0.0f;
+                        const float cc = (keep ? cand : 0.0f) * live[i];
+                        const bool take = keep && (live[i] != 0.0f);
+                        T[i] = take ? testT : T[i];
+                        Cr[i] = fmaf(cc, q1.z, Cr[i]);
+                        Cg[i] = fmaf(cc, q1.w, Cg[i]);
+                        Cb[i] = fmaf(cc, q2.x, Cb[i]);
+                        D[i] = fmaf(cc, depth, D[i]);
+                        ID[i] = fmaf(cc, idepth, ID[i]);
+                        c4[i] = cc;
+                    }
+                    const float v = fmaxf(fmaxf(c4[0], c4[1]), fmaxf(c4[2], c4[3]));
+                    if (__any_sync(FULLM, v > 0.0f)) {
+                        const uint32_t vb = __float_as_uint(v);
+                        const uint32_t wm = __reduce_max_sync(FULLM, vb);
+                        const int i = (c4[0] == v) ? 0 : (c4[1] == v) ? 1 : (c4[2] == v) ? 2 : 3;
+                        const uint32_t pk = (vb == wm) ? (0xFFFFFFFFu - (uint32_t)(pix_base + i)) : 0u;
+                        const uint32_t wp = __reduce_max_sync(FULLM, pk);
+                        if (lane == 0) s_best[warp][j] = ((unsigned long long)wm << 32) | (unsigned long long)wp;
+                    }
+                    ++iters;
                 }
-                const float v = fmaxf(fmaxf(c4[0], c4[1]), fmaxf(c4[2], c4[3]));
-                if (__any_sync(FULLM, v > 0.0f)) {
-                    const uint32_t vb = __float_as_uint(v);
-                    const uint32_t wm = __reduce_max_sync(FULLM, vb);
-                    const int i = (c4[0] == v) ? 0 : (c4[1] == v) ? 1 : (c4[2] == v) ? 2 : 3;
-                    const uint32_t pk = (vb == wm) ? (0xFFFFFFFFu - (uint32_t)(pix_base + i)) : 0u;
-                    const uint32_t wp = __reduce_max_sync(FULLM, pk);
-                    if (lane == 0) s_best[warp][j] = ((unsigned long long)wm << 32) | (unsigned long long)wp;
-                }
+                if (SURF && (members & 255) == 0) flush_round(256);
             }
-            iters += (unsigned long long)nload;
-            const float lmax = fmaxf(fmaxf(live[0], live[1]), fmaxf(live[2], live[3]));
-            warp_done = __all_sync(FULLM, lmax == 0.0f);
+            if (!warp_done) {
+                const float lmax = fmaxf(fmaxf(live[0], live[1]), fmaxf(live[2], live[3]));
+                warp_done = __all_sync(FULLM, lmax == 0.0f);
+            }
         }
         __syncthreads();
+        // one atomic per entry for the whole super-tile: the best (contribution, pixel) over its warps.  (Tried: every
+        // warp straight to the global maximum and a single barrier per chunk — 10 % slower on C4.)
         for (int t = tid; t < nload; t += TBT) {
             unsigned long long best = s_best[0][t];
             s_best[0][t] = 0ull;
@@ -518,45 +605,10 @@ __global__ void __launch_bounds__(TBT, 12) blend_tiles_kernel(const TileBlendPar
                 s_best[w][t] = 0ull;
                 best = o > best ? o : best;
             }
-            const uint32_t gid = s_gid[c % 3][t];
-            if ((best >> 32) != 0ull) atomicMax(p.cam_best + gid, best);
-            if (SURF) {
-                s_rdepth[(c & 1) * TCH + t] = q2s[t].y;
-                s_rgid[(c & 1) * TCH + t] = gid;
-            }
-        }
-        if (SURF && ((c & 1) == 1 || !more)) {
-            // end of a 256-entry round (forward.cu:460-477): distance of every entry of the round to the nearest running
-            // expected depth among the tile's threads.  Sort the (<= 256) values once, then binary-search per entry.
-            const int nround = ((c & 1) == 1 ? TCH : 0) + nload;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) s_E[tid * 4 + i] = valid[i] ? D[i] : 3.0e38f;
-            __syncthreads();
-            for (int k = 2; k <= 256; k <<= 1)
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int i = tid; i < 256; i += TBT) {
-                        const int ixj = i ^ j;
-                        if (ixj > i) {
-                            const float a = s_E[i], b = s_E[ixj];
-                            const bool up = (i & k) == 0;
-                            if ((a > b) == up) { s_E[i] = b; s_E[ixj] = a; }
-                        }
-                    }
-                    __syncthreads();
-                }
-            for (int t = tid; t < nround; t += TBT) {
-                const float d = s_rdepth[t];
-                int lo = 0, hi = 256;  // first index with E >= d
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_E[mid] < d) lo = mid + 1; else hi = mid; }
-                float best = 3.0e38f;
-                if (lo < 256 && s_E[lo] < 1.0e38f) best = fabsf(s_E[lo] - d);
-                if (lo > 0 && s_E[lo - 1] < 1.0e38f) best = fminf(best, fabsf(d - s_E[lo - 1]));
-                if (tile_has_outside) best = fminf(best, fabsf(d));  // threads outside the image hold expected depth 0
-                if (best < 1.0e38f) atomicMin(p.cam_dist + s_rgid[t], __float_as_uint(best));
-            }
-            __syncthreads();
+            if ((best >> 32) != 0ull) atomicMax(p.cam_best + gids[t], best);
         }
     }
+    if (SURF && !tile_left && (members & 255) != 0) flush_round(members & 255);  // the last, partial round
     // out_color = C + T * bg, depth, inverse depth for the pixels that are inside the image and not masked (:485-496)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -643,10 +695,11 @@ extern "C" int g2pc_tiles_preprocess(const void* geom, const float* colours, con
     p.focal_y = (float)p.H / (2.0f * p.tan_fovy);  // rasterizer_impl.cu:229-230
     p.focal_x = (float)p.W / (2.0f * p.tan_fovx);
     p.gx = (p.W + TILE - 1) / TILE; p.gy = (p.H + TILE - 1) / TILE;
+    p.sgx = (p.gx + 1) / 2; p.sgy = (p.gy + 1) / 2;
     G2PC_CHECK_ARG(p.gx <= 256 && p.gy <= 256, "image larger than 4096 pixels per side (packed tile rect)");
     p.proj = (float4*)proj; p.node_cnt = node_cnt; p.depth_key = depth_key; p.val = (unsigned long long*)val;
     p.radii = radii;
-    const int ntiles = p.gx * p.gy;
+    const int ntiles = p.sgx * p.sgy;
     p.use_hist = ntiles <= 24 * 1024 ? 1 : 0;
     const size_t smem = p.use_hist ? (size_t)ntiles * sizeof(uint32_t) : 0;
     if (smem > 48 * 1024)
@@ -664,7 +717,8 @@ extern "C" int g2pc_tiles_build(uint32_t* node_cnt, int32_t width, int32_t heigh
     G2PC_CHECK_ARG(width > 0 && height > 0 && max_leaves >= 1 && frame >= 0, "bad sizes");
     TileTreeParams p;
     p.node_cnt = node_cnt; p.leaves = leaves; p.leaf_order = leaf_order;
-    p.W = width; p.H = height; p.gx = (width + TILE - 1) / TILE; p.gy = (height + TILE - 1) / TILE;
+    p.W = width; p.H = height;
+    p.gx = ((width + TILE - 1) / TILE + 1) / 2; p.gy = ((height + TILE - 1) / TILE + 1) / 2;  // super-tile grid
     p.max_leaves = max_leaves; p.inst_capacity = inst_capacity; p.matrix_capacity = matrix_capacity;
     p.ms_rows = ms_rows; p.frame = frame; p.header = header; p.fail = fail; p.work_counters = work_counters;
     tile_tree_kernel<<<1, TB, 0, (cudaStream_t)stream>>>(p);
@@ -688,15 +742,16 @@ extern "C" int g2pc_tiles_blend(const g2pc_leaf_t* leaves, const int32_t* leaf_o
     p.W = width; p.H = height;
     for (int i = 0; i < 3; ++i) p.bg[i] = background3_host[i];
     p.work_counter = work_counters; p.stats = (unsigned long long*)stats;
-    int dev = 0, sms = 148, per_sm = 8;
+    int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaStream_t st = (cudaStream_t)stream;
+    int per_sm = 3;
     if (cam_dist) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blend_tiles_kernel<true>, TBT, 0) != cudaSuccess || per_sm < 1) per_sm = 8;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blend_tiles_kernel<true>, TBT, 0) != cudaSuccess || per_sm < 1) per_sm = 3;
         blend_tiles_kernel<true><<<(unsigned)(sms * per_sm), TBT, 0, st>>>(p);
     } else {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blend_tiles_kernel<false>, TBT, 0) != cudaSuccess || per_sm < 1) per_sm = 8;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blend_tiles_kernel<false>, TBT, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
         blend_tiles_kernel<false><<<(unsigned)(sms * per_sm), TBT, 0, st>>>(p);
     }
     G2PC_CHECK_LAUNCH();

@@ -148,7 +148,7 @@ class GaussianRasterizer(FrameQueue):
             self._cam_dist = torch.empty((m,), dtype=torch.int32, device=dev)
             capi.call("g2pc_fill_u32", capi.ptr(self._cam_dist), FLT_MAX_BITS, m, capi.stream_ptr(dev))
         self._stats = torch.zeros((capi.STAT_WORDS,), dtype=torch.int64, device=dev)
-        self._inst_cap = max(12 * n, 1 << 16)  # 16x16 tiles: a splat of radius ~15 px touches 9-16 of them
+        self._inst_cap = max(8 * n, 1 << 16)  # 32x32 super-tiles: a splat of radius ~15 px touches 4-9 of them
         self._res = {}
         self._last_slot = 0
         self.last_stats = {}
@@ -173,7 +173,8 @@ class GaussianRasterizer(FrameQueue):
         t = self._res.get((W, H))
         if t is None:
             dev = self.device
-            gx, gy = (W + TILE - 1) // TILE, (H + TILE - 1) // TILE
+            # the depth-ordered lists are built per super-tile of 2x2 tiles (csrc/s7_tiles.cu)
+            gx, gy = ((W + TILE - 1) // TILE + 1) // 2, ((H + TILE - 1) // TILE + 1) // 2
             ntiles = gx * gy
             chunk = int(self.lib.g2pc_multisplit_chunk(ntiles))
             if chunk <= 0:

@@ -25,6 +25,7 @@ ap.add_argument("--cams", type=int, default=3)
 ap.add_argument("--first-cam", type=int, default=0)
 ap.add_argument("--renderer", default="python")
 ap.add_argument("--strict", action="store_true")
+ap.add_argument("--surface", action="store_true", help="renderer cuda: also compute the surface distances (C4)")
 a = ap.parse_args()
 wl = bench.WORKLOADS[a.workload]
 dev = "cuda:0"
@@ -32,7 +33,8 @@ sc = bench._scene_for(wl)
 d = {k: v.to(dev) for k, v in sc.items()}
 G = gh.Gaussians(d["xyz"], d["scales"], d["rots"], d["colours"], d["opacities"])
 R = gr.get_renderer(a.renderer, G.xyz, G.opacities.unsqueeze(1), G.colours, G.covariances,
-                    shs=d["shs"] if wl["sh"] > 0 else None, visible_gaussian_threshold=0.05)
+                    shs=d["shs"] if wl["sh"] > 0 else None, visible_gaussian_threshold=0.05,
+                    **(dict(calculate_surface_distance=True, surface_distance_std=2.0) if a.surface else {}))
 if a.strict:
     R.t_stop = 0.0
 R.async_mode = True
