@@ -230,25 +230,40 @@ __global__ void __launch_bounds__(1024, 1) preprocess_kernel(const PreParams p) 
             });
         }
     }
-    if (has_rect && bxlo <= bxhi) {
-        // deeper candidate levels exist only after a count-driven split asked for them (rare): per lane
-        for (int l = p.base_level + 1; l < p.meta.num_levels; ++l) {
-            if (!((p.level_mask >> l) & 1u)) continue;
-            const int o1 = (1 << l) - 1;
+    const bool in_tree = has_rect && bxlo <= bxhi;
+    // deeper candidate levels exist only after a count-driven split asked for them (1920 px / 6 M Gaussians: two of them,
+    // ~40 nodes per Gaussian): the same warp-cooperative walk as the base level when the level is clean
+    for (int l = p.base_level + 1; l < p.meta.num_levels; ++l) {  // (uniform)
+        if (!((p.level_mask >> l) & 1u)) continue;
+        const int o1 = (1 << l) - 1;
+        int xlo = 1, xhi = 0, ylo = 1, yhi = 0;
+        if (in_tree) {
             const uint16_t* L = s_lut + l * lut_level;
-            const int xlo = L[qx0], xhi = (int)L[p.cam.width + cx1] - 1;
-            const int ylo = L[2 * p.cam.width + qy0], yhi = (int)L[2 * p.cam.width + p.cam.height + cy1] - 1;
-            if (xlo > xhi || ylo > yhi) continue;
-            uint32_t* cnt = p.node_cnt + off2(l);
-            for (int iy = ylo; iy <= yhi; ++iy) {
-                if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy)) continue;
-                for (int ix = xlo; ix <= xhi; ++ix) {
-                    if (!axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) continue;
-                    if (use_hist) atomicAdd(s_hist + off2(l) + (iy << l) + ix, 1u);
-                    else atomicAdd(cnt + (iy << l) + ix, 1u);
-                }
+            xlo = L[qx0]; xhi = (int)L[p.cam.width + cx1] - 1;
+            ylo = L[2 * p.cam.width + qy0]; yhi = (int)L[2 * p.cam.width + p.cam.height + cy1] - 1;
+        }
+        const bool some = xlo <= xhi && ylo <= yhi;
+        uint32_t* cnt = p.node_cnt + off2(l);
+        uint32_t* hcnt = s_hist + off2(l);  // (kept apart: shared-memory atomics, not generic ones)
+        if (((p.clean_mask >> l) & 1u) && l <= G2PC_RANGE_MAX_LEVEL) {
+            const uint32_t rl = some ? g2pc_pack_range(xlo, xhi, ylo, yhi) : (uint32_t)G2PC_RANGE_EMPTY;
+            warp_for_each_node(rl, 0u, [&](int ix, int iy, int, uint32_t) {
+                if (use_hist) atomicAdd(hcnt + (iy << l) + ix, 1u);
+                else atomicAdd(cnt + (iy << l) + ix, 1u);
+            });
+            continue;
+        }
+        if (!some) continue;
+        for (int iy = ylo; iy <= yhi; ++iy) {
+            if (!axis_member(T.ys + o1, T.ye + o1, T.yf + o1, iy)) continue;
+            for (int ix = xlo; ix <= xhi; ++ix) {
+                if (!axis_member(T.xs + o1, T.xe + o1, T.xf + o1, ix)) continue;
+                if (use_hist) atomicAdd(hcnt + (iy << l) + ix, 1u);
+                else atomicAdd(cnt + (iy << l) + ix, 1u);
             }
         }
+    }
+    if (in_tree) {
         // levels above: every node splits by its size, only "is anything in it" matters (an empty tile is background
         // and has no children, gauss_render.py:313-315).  A child tile may overhang its parent by a pixel, so this is
         // NOT implied by the leaf-level counts: look the exact range of every level up and raise plain flags.

@@ -264,6 +264,7 @@ struct MsParams {
     uint32_t* inst_gid;
     int32_t leaf_cap;      // leaves the shared-memory tables are sized for (<= max_leaves of the tree)
     int32_t base_clean;    // the base level has no dropped / degenerate node: membership = the packed range, no table look-ups
+    uint32_t clean_mask;   // the same, per level
     int32_t grid_w;        // > 0: flat tile grid (s7_tiles.cu): leaf = iy * grid_w + ix, the packed range is the tile rect
 };
 
@@ -295,7 +296,10 @@ __device__ __forceinline__ void for_each_leaf(const MsParams& p, const QtTables&
     if (p.meta.num_levels <= lb + 1) return;
     int xlo, xhi, ylo, yhi;
     g2pc_unpack_range(range, xlo, xhi, ylo, yhi);
-    // ---- count-driven splits below the base level (rare): per lane ----
+    // ---- count-driven splits below the base level ----
+    // Rare at 1280 px; at 1920 px with 6 M Gaussians most of the sphere's base nodes split two levels down (C5: 150 M
+    // instances per camera, almost all from here), so the deeper levels get the same warp-cooperative walk as the base
+    // level (per-lane loops with per-node table checks ran at 5 of 32 threads: 69 + 13 ms per camera, ncu r02g).
     // combine the flags raised on behalf of each owner
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) deeper |= __shfl_xor_sync(0xffffffffu, deeper, o);
@@ -309,21 +313,34 @@ __device__ __forceinline__ void for_each_leaf(const MsParams& p, const QtTables&
             for (int ix = ex; ix <= xhi; ++ix)
                 if ((iy < ylo || ix < xlo) && s_leaf[(iy << lb) + ix] == -2) mine = true;
     }
-    if (!mine) return;
-    const float4 q0 = __ldg(p.proj + 3 * (int64_t)gid);
-    const float4 q2 = __ldg(p.proj + 3 * (int64_t)gid + 2);
-    float x0, x1, y0, y1;
-    gaussian_rect(q0.x, q0.y, q2.z, p.width, p.height, x0, x1, y0, y1);
+    if (!__any_sync(0xffffffffu, mine)) return;
+    float x0 = 0.f, x1 = 0.f, y0 = 0.f, y1 = 0.f;
+    if (mine) {
+        const float4 q0 = __ldg(p.proj + 3 * (int64_t)gid);
+        const float4 q2 = __ldg(p.proj + 3 * (int64_t)gid + 2);
+        gaussian_rect(q0.x, q0.y, q2.z, p.width, p.height, x0, x1, y0, y1);
+    }
     const float isx0 = 1.0f / (float)p.width, isy0 = 1.0f / (float)p.height;
-    for (int l = lb + 1; l < p.meta.num_levels; ++l) {
+    for (int l = lb + 1; l < p.meta.num_levels; ++l) {  // (uniform)
         if (!((p.level_mask >> l) & 1u)) continue;
         const int ol = (1 << l) - 1;
-        int axlo, axhi, aylo, ayhi;
-        axis_range(T.xs + ol, T.xe + ol, l, x0, x1, isx0 * (float)(1 << l), axlo, axhi);
-        if (axlo > axhi) continue;
-        axis_range(T.ys + ol, T.ye + ol, l, y0, y1, isy0 * (float)(1 << l), aylo, ayhi);
-        if (aylo > ayhi) continue;
+        int axlo = 1, axhi = 0, aylo = 1, ayhi = 0;
+        if (mine) {
+            axis_range(T.xs + ol, T.xe + ol, l, x0, x1, isx0 * (float)(1 << l), axlo, axhi);
+            if (axlo <= axhi) axis_range(T.ys + ol, T.ye + ol, l, y0, y1, isy0 * (float)(1 << l), aylo, ayhi);
+        }
+        const bool some = axlo <= axhi && aylo <= ayhi;
         const int32_t* nl = p.node_leaf + off2d(l);
+        if (((p.clean_mask >> l) & 1u) && l <= G2PC_RANGE_MAX_LEVEL) {
+            // no dropped / degenerate node at this level: membership = the range; cooperative walk
+            const uint32_t rl = some ? g2pc_pack_range(axlo, axhi, aylo, ayhi) : (uint32_t)G2PC_RANGE_EMPTY;
+            warp_for_each_node(rl, gid, [&](int ix, int iy, int owner, uint32_t og) {
+                const int32_t v = __ldg(nl + (iy << l) + ix);
+                if (v >= 0) f(v, owner, og);
+            });
+            continue;
+        }
+        if (!some) continue;
         for (int iy = aylo; iy <= ayhi; ++iy) {
             if (!axis_member(T.ys + ol, T.ye + ol, T.yf + ol, iy)) continue;
             for (int ix = axlo; ix <= axhi; ++ix) {
@@ -613,6 +630,7 @@ extern "C" int g2pc_multisplit(const uint64_t* val_sorted, int64_t n, const void
     p.inst_gid = inst_gid;
     p.leaf_cap = leaf_cap; p.grid_w = 0;
     p.base_clean = (int32_t)((clean_mask >> p.base_level) & 1u);
+    p.clean_mask = clean_mask;
     const int32_t chunks = (int32_t)((n + C - 1) / C);
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 256) return launch_multisplit<256>(p, chunks, st);
@@ -640,7 +658,7 @@ extern "C" int g2pc_multisplit_grid(const uint64_t* val_sorted, int64_t n, int32
     p.level_mask = 1u; p.base_level = 0;
     p.node_leaf = nullptr; p.header = header; p.fail = fail; p.frame = frame; p.leaves = leaves; p.matrix = matrix;
     p.inst_gid = inst_gid;
-    p.leaf_cap = leaf_cap; p.grid_w = grid_w; p.base_clean = 1;
+    p.leaf_cap = leaf_cap; p.grid_w = grid_w; p.base_clean = 1; p.clean_mask = 1u;
     const int32_t chunks = (int32_t)((n + C - 1) / C);
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 256) return launch_multisplit<256>(p, chunks, st);

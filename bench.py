@@ -303,7 +303,7 @@ def run_ours(args):
                                f"width {wl['res']}, SH deg {wl['sh']}, visibility_threshold 0.05, renderer_type={rtype} "
                                "semantics", "points_out": npts,
                    "blend_t_stop": config.BLEND_T_STOP, "frame_slots": config.FRAME_SLOTS,
-                   "l2": ("inputs larger than L2 (per-step working set >> 126 MB)" if h2d_bytes > 4 * 126e6 else
+                   "l2": ("inputs larger than L2 (per-step working set >> 126 MB)" if h2d_bytes * world > 4 * 126e6 else
                           "working set below L2 and not flushed (non-headline workload)"),
                    "parallelism": "1 GPU" if world == 1 else f"cameras sharded x{world} (colour), Gaussians sharded x{world} (sampling)"},
         "e2e": {"value": round(e2e_pts / (e2e_step * 1e-3) / 1e6, 3), "unit": UNIT, "ms_per_step": round(e2e_step, 3),

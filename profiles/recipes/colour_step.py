@@ -25,6 +25,7 @@ ap.add_argument("--cams", type=int, default=3)
 ap.add_argument("--first-cam", type=int, default=0)
 ap.add_argument("--renderer", default="python")
 ap.add_argument("--strict", action="store_true")
+ap.add_argument("--sync", action="store_true", help="confirm every frame before the next (no skipped launches after a replay)")
 ap.add_argument("--surface", action="store_true", help="renderer cuda: also compute the surface distances (C4)")
 a = ap.parse_args()
 wl = bench.WORKLOADS[a.workload]
@@ -37,7 +38,7 @@ R = gr.get_renderer(a.renderer, G.xyz, G.opacities.unsqueeze(1), G.colours, G.co
                     **(dict(calculate_surface_distance=True, surface_distance_std=2.0) if a.surface else {}))
 if a.strict:
     R.t_stop = 0.0
-R.async_mode = True
+R.async_mode = not a.sync
 cams, intr = synth.make_cameras(wl["cams"])
 for c, k in list(zip(cams, intr))[a.first_cam:a.first_cam + a.cams]:
     R(ch.get_camera(a.renderer, c, k, colour_resolution=wl["res"]))
