@@ -19,6 +19,9 @@ import torch
 from . import capi, config
 
 
+_HDR_POOLS = {}  # device -> free pinned frame headers (cudaHostAlloc is slow: never once per renderer)
+
+
 class FrameQueue:
     """Mixin.  The owner provides: self.device, self._ensure_buffers(camera, slot) (allocate / grow the slot's scratch on
     the current stream), self._enqueue_front(camera, frame, slot) -> device header tensor,
@@ -28,7 +31,7 @@ class FrameQueue:
     def _init_frames(self):
         self._frame = 0
         self._pending = []   # (frame, camera, camera_index, pinned header, end-of-frame event)
-        self._hdr_pool = []
+        self._hdr_pool = _HDR_POOLS.setdefault(str(self.device), [])  # pinned headers are shared by all renderers
         self.replays = 0
         self.async_mode = False
         self.num_slots = max(1, int(config.FRAME_SLOTS))

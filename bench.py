@@ -86,29 +86,47 @@ def settings_for(wl, g2p, device, renderer=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons, one sample every 200 ms.  ONE process per node (local rank 0) watches the
+    GPUs of all local ranks; it is started before the warm-up so that its start-up (NVML initialisation, hundreds of ms
+    of driver traffic) stays out of the timed region, and only the samples taken between mark_begin() and mark_end() are
+    reported."""
 
-    def __init__(self, index=0):
-        self.index = index
+    def __init__(self, indices=(0,), enabled=True):
+        self.indices = list(indices)
+        self.enabled = enabled
         self.rows = []
         self.proc = None
+        self.t0 = self.t1 = None
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "--id=" + ",".join(str(i) for i in self.indices),
+                                          f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            # NVML start-up stalls every GPU of the node for tens of ms (seen as one 220 ms step among 150 ms ones at
+            # N=2): wait for the first sample, i.e. until the tool is in its steady 200 ms polling loop
+            t_end = time.time() + 10.0
+            while not self.rows and time.time() < t_end and self.proc.poll() is None:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
         return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.strip().split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.strip().split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def __exit__(self, *exc):
         if self.proc is not None:
@@ -120,12 +138,13 @@ class ClockSampler:
         return False
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.25)]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "gpus_watched": self.indices}
 
 
 def _peaks():
@@ -233,8 +252,9 @@ def run_ours(args):
             if dbg:
                 t1 = time.perf_counter()
                 torch.cuda.synchronize()
-                print(f"[rank {rank}] {fn.__name__}: host {1e3 * (t1 - t0):.1f} ms, +drain {1e3 * (time.perf_counter() - t1):.1f} ms",
-                      file=sys.stderr, flush=True)
+                ph = getattr(sys.modules.get("g2pc.dist"), "LAST_PHASES", None) if world > 1 else None
+                print(f"[rank {rank}] {fn.__name__}: host {1e3 * (t1 - t0):.1f} ms, +drain {1e3 * (time.perf_counter() - t1):.1f} ms"
+                      + (f" phases {({k: round(v, 1) for k, v in ph.items()})}" if ph else ""), file=sys.stderr, flush=True)
         b.record()
         barrier()
         ms = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
@@ -244,11 +264,15 @@ def run_ours(args):
             dist.all_reduce(npts, op=dist.ReduceOp.SUM)
         return float(ms.item()), int(npts.item()), pc
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    capi.LAUNCHES = 0
-    with ClockSampler(local) as clk:
+    # (torchrun: LOCAL_WORLD_SIZE ranks on this node; their GPUs are 0..LOCAL_WORLD_SIZE-1)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    with ClockSampler(range(local_world), enabled=(local == 0)) as clk:
+        for _ in range(max(args.warmup, 3)):
+            step_resident()
+        capi.LAUNCHES = 0
+        clk.mark_begin()
         ms, npts, pc = timed(step_resident, args.steps)
+        clk.mark_end()
     launches = capi.LAUNCHES
     ms_step = ms / args.steps
     value = npts / (ms_step * 1e-3) / 1e6
