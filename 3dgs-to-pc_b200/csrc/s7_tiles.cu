@@ -13,8 +13,8 @@
 // 3600 — the multisplit's cost grows with the number of lists); the blend of a tile walks its super-tile's list and skips
 // the entries whose tile rect (packed into the projection record) does not contain the tile, so every tile still sees
 // exactly its own list, in order, and the 256-entry rounds of the surface distance count the tile's own entries;
-// the blend is a persistent kernel with TMA-staged id chunks, cp.async record gathers and packed FP32x2 arithmetic, and
-// every cross-thread reduction is a deterministic max / min (the reference's shared-memory CAS loop, its racing
+// the blend is a persistent kernel with TMA-staged id chunks and cp.async record gathers (scalar FP32: the per-pixel keep /
+// stop predicates of these semantics do not pack into FP32x2), and every cross-thread reduction is a deterministic max / min (the reference's shared-memory CAS loop, its racing
 // `largest_collected_contribution_pixel` store and its non-atomic cross-block updates make its results run-dependent —
 // SURVEY.md §2.1).  Deterministic definition of the surface distance: after every round of 256 list entries
 // of a tile, dist(j) = min over the tile's pixel threads of |depth_j - E_p| with E_p the thread's running un-normalised
@@ -190,8 +190,9 @@ __global__ void __launch_bounds__(256) preprocess_tiles_kernel(const TilePrePara
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Tile table (one CTA): every tile is a "leaf" (leaf index = tile index, row-major), lists padded to 16 bytes, heaviest
-// tiles first in the launch order, frame header + poison exactly as g2pc_build_tree.
+// List table (one CTA): every super-tile is a "leaf" (leaf index = super-tile index, row-major; the leaf rectangle is its
+// 32x32 pixels clipped to the image), lists padded to 16 bytes, heaviest first in the launch order, frame header + poison
+// exactly as g2pc_build_tree.
 constexpr int TB = 1024;
 constexpr int SORT_CAP = 8192;
 

@@ -291,7 +291,10 @@ int g2pc_compose_image(uint32_t* owner, const float* leaf_colour, int32_t width,
  * CudaRasterizer::Rasterizer::forward, rasterizer_impl.cu:197-352: preprocessCUDA forward.cu:153-271, duplicateWithKeys /
  * radix sort / identifyTileRanges rasterizer_impl.cu:69-137,285-326, renderCUDA forward.cu:303-497) and the accumulator
  * updates of GaussianRasterizer.forward (gaussian_pointcloud_rasterization/__init__.py:126-158).
- * One camera = tiles_preprocess -> depth_sort -> tiles_build -> multisplit_grid -> tiles_blend -> tiles_accumulate. */
+ * One camera = tiles_preprocess -> depth_sort -> tiles_build -> multisplit_grid -> tiles_blend -> tiles_accumulate.
+ * The depth-ordered lists are built per SUPER-TILE of 2x2 tiles (32x32 pixels; grid SW x SH = ceil(ceil(W/16)/2) x
+ * ceil(ceil(H/16)/2)); the blend of a tile walks its super-tile's list and skips the entries whose tile rect (packed into
+ * the projection record) does not contain the tile, so every tile sees exactly the reference's per-tile list. */
 typedef struct {
     float viewmatrix[16];  /* world->view, row-vector convention, z forward (camera_handler.py:75,91), row-major */
     float projmatrix[16];  /* viewmatrix @ projection (camera_handler.py:100), row-major */
@@ -303,19 +306,19 @@ typedef struct {
 /* preprocessCUDA: near cull z_view <= 0.2, EWA covariance + 0.3, conic, radius = ceil(3 sqrt(lambda_max)), tile rect
  * (16x16 tiles), colour given or SH deg <= 3 (sh_layout 0: (n,3,stride) channel-major as the loader yields it,
  * gauss_dataloader.py:42-44; 1: (n,stride,3) coefficient-major as forward.cu:31 reads it).  Outputs as g2pc_preprocess
- * (proj records, depth_key = bits(z_view), val = packed tile rect << 32 | index, node_cnt = Gaussians per tile);
- * radii (n) int32 or NULL. */
+ * (proj records — the last word holds the packed TILE rect; depth_key = bits(z_view); val = packed SUPER-TILE rect << 32 |
+ * index; node_cnt (SW*SH, zeroed by the caller / by tiles_build) = Gaussians per super-tile); radii (n) int32 or NULL. */
 int g2pc_tiles_preprocess(const void* geom, const float* colours, const float* shs, int32_t sh_stride,
                           int32_t sh_degree, int32_t sh_layout, int64_t n, const g2pc_raster_t* rs_host, void* proj,
                           uint32_t* node_cnt, uint32_t* depth_key, uint64_t* val, int32_t* radii, void* stream);
 
-/* Tile table: every tile of the ceil(W/16) x ceil(H/16) grid is a leaf (leaf index = tile index, row-major); list
- * offsets, launch order, frame header / poison as g2pc_build_tree; clears node_cnt and work_counters. */
+/* List table: every super-tile of the SW x SH grid is a leaf (leaf index = super-tile index, row-major; max_leaves >=
+ * SW*SH); list offsets, launch order, frame header / poison as g2pc_build_tree; clears node_cnt and work_counters. */
 int g2pc_tiles_build(uint32_t* node_cnt, int32_t width, int32_t height, g2pc_leaf_t* leaves, int32_t* leaf_order,
                      int32_t max_leaves, int64_t inst_capacity, int64_t matrix_capacity, int32_t ms_rows, int32_t frame,
                      int32_t* header, uint32_t* fail, int32_t* work_counters, void* stream);
 
-/* g2pc_multisplit over the tile grid (the packed range is the tile rect). */
+/* g2pc_multisplit over a flat grid (grid_w x grid_h = SW x SH here; the packed range is the rect in grid cells). */
 int g2pc_multisplit_grid(const uint64_t* val_sorted, int64_t n, int32_t grid_w, int32_t grid_h,
                          const g2pc_leaf_t* leaves, const int32_t* header, const uint32_t* fail, int32_t frame,
                          int32_t leaf_cap, uint32_t* matrix, uint32_t* inst_gid, void* stream);
